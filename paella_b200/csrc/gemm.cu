@@ -1,0 +1,407 @@
+// tcgen05 GEMM for every Linear / 1x1-conv / patchify contraction on the path:
+//     C[M,N] = A[M,K] . W[N,K]^T   (fp16 operands, fp32 accumulation in TMEM)  + fused epilogue
+// Replaces the cuBLAS/cuDNN calls behind nn.Linear / nn.Conv2d(k=1) / Conv2d(k=2,s=2) /
+// ConvTranspose2d(k=2,s=2) in ref/src/modules.py (ResBlock :49-55, AttnBlock :71-74, embedding :130-134,
+// resamplers :153-156,172-175, clf/out_mapper :179-187) and ref/src/vqgan.py (ResBlock :16-20).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0   : TMA producer  — cp.async.bulk.tensor 2D loads of 128x64 (A) and BLOCK_Nx64 (W) fp16 tiles,
+//              128B-swizzled, into a STAGES-deep shared-memory ring guarded by full/empty mbarriers
+//   warp 1   : MMA issuer    — one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per stage into one of
+//              two TMEM accumulator buffers; tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2-5: epilogue      — tcgen05.ld 32x32b (thread = row, registers = columns), fused bias / GELU+GRN
+//              statistics / residual+FiLM / un-patchify scatter / NCHW transpose, vectorised global stores;
+//              overlaps with the next tile's MMAs through the second TMEM buffer.
+#include "gemm.cuh"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace pb {
+
+// ------------------------------------------------------------------ tensor maps (host)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+int make_tmap_f16_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    PB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    PB_CHECK(((uintptr_t)ptr & 15) == 0, "TMA: base pointer must be 16-byte aligned");
+    PB_CHECK((ld * 2) % 16 == 0, "TMA: row stride %lld halves is not a multiple of 16 bytes", (long long)ld);
+    PB_CHECK(box_rows >= 1 && box_rows <= 256, "TMA: bad box rows %d", box_rows);
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r,
+             (long long)rows, (long long)cols, (long long)ld, box_rows);
+    return 0;
+}
+
+// ------------------------------------------------------------------ epilogue
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, int M, int N, int row, int col0,
+                                               float (&v)[32], int lane) {
+    const bool row_ok = row < M;
+    // ---- bias
+    if (MODE != PB200_EPI_UNPATCH_F32) {
+        if (ep.bias) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                if (col0 + g * 4 < N) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + g * 4));
+                    v[g * 4 + 0] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
+                }
+            }
+        }
+    }
+    if (MODE == PB200_EPI_F16 || MODE == PB200_EPI_F32) {
+        if (!row_ok) return;
+        int64_t orow = row;
+        if (ep.remap_in > 0) orow = (int64_t)(row / ep.remap_in) * ep.remap_out + (row % ep.remap_in);
+        if (MODE == PB200_EPI_F16) {
+            __half* o = reinterpret_cast<__half*>(ep.out) + orow * ep.ldo + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (col0 + g * 8 < N) {
+                    uint4 pk;
+                    pk.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
+                    pk.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
+                    *reinterpret_cast<uint4*>(o + g * 8) = pk;
+                }
+        } else {
+            float* o = reinterpret_cast<float*>(ep.out) + orow * ep.ldo + col0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                if (col0 + g * 4 < N)
+                    *reinterpret_cast<float4*>(o + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        }
+    } else if (MODE == PB200_EPI_GELU_F16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        if (row_ok) {
+            __half* o = reinterpret_cast<__half*>(ep.out) + (int64_t)row * ep.ldo + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (col0 + g * 8 < N) {
+                    uint4 pk;
+                    pk.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
+                    pk.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
+                    *reinterpret_cast<uint4*>(o + g * 8) = pk;
+                }
+        }
+        if (ep.sqsum) {   // GlobalResponseNorm statistic: sum over the sample's positions of h^2, per channel
+            const int P = ep.rows_per_sample;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (row_ok && col0 + j < N) ? v[j] * v[j] : 0.f;
+            if ((P & 31) == 0) {
+                // transpose-reduce over the warp's 32 rows: lane j ends with the column-(col0+j) sum
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int i = 0; i < o; ++i) {
+                        const bool up = (lane & o) != 0;
+                        const float send = up ? v[i] : v[i + o];
+                        const float keep = up ? v[i + o] : v[i];
+                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                    }
+                }
+                const int row0 = row - lane;
+                if (row0 < M && col0 + lane < N)
+                    atomicAdd(ep.sqsum + (int64_t)(row0 / P) * N + col0 + lane, v[0]);
+            } else if ((P & (P - 1)) == 0 && P < 32) {
+                for (int o = P >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+                }
+                if (row_ok && (lane & (P - 1)) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < N) atomicAdd(ep.sqsum + (int64_t)(row / P) * N + col0 + j, v[j]);
+                }
+            } else if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < N) atomicAdd(ep.sqsum + (int64_t)(row / P) * N + col0 + j, v[j]);
+            }
+        }
+    } else if (MODE == PB200_EPI_RESID_F32) {
+        if (!row_ok) return;
+        const float* r = ep.resid + (int64_t)row * ep.ldr + col0;
+        float* o = reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col0;
+        const float* fa = nullptr;
+        if (ep.film) fa = ep.film + (int64_t)(row / ep.rows_per_sample) * ep.film_ld + ep.film_off + col0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            if (col0 + g * 4 < N) {
+                const float4 rr = *reinterpret_cast<const float4*>(r + g * 4);
+                float4 y;
+                y.x = fmaf(v[g * 4 + 0], ep.alpha, rr.x); y.y = fmaf(v[g * 4 + 1], ep.alpha, rr.y);
+                y.z = fmaf(v[g * 4 + 2], ep.alpha, rr.z); y.w = fmaf(v[g * 4 + 3], ep.alpha, rr.w);
+                if (fa) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(fa + g * 4));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(fa + N + g * 4));
+                    y.x = fmaf(y.x, 1.0f + a.x, b.x); y.y = fmaf(y.y, 1.0f + a.y, b.y);
+                    y.z = fmaf(y.z, 1.0f + a.z, b.z); y.w = fmaf(y.w, 1.0f + a.w, b.w);
+                }
+                *reinterpret_cast<float4*>(o + g * 4) = y;
+            }
+        }
+    } else if (MODE == PB200_EPI_UNPATCH_F32) {
+        if (!row_ok) return;
+        const int hw = ep.up_h * ep.up_w;
+        const int b = row / hw, rem = row - b * hw;
+        const int y = rem / ep.up_w, x = rem - y * ep.up_w;
+        float* obase = reinterpret_cast<float*>(ep.out);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const int col = col0 + g * 4;
+            if (col < N) {
+                const int q = col / ep.up_cout, co = col - q * ep.up_cout;    // q = dy*2+dx
+                const int64_t orow = ((int64_t)b * 2 * ep.up_h + 2 * y + (q >> 1)) * (2 * ep.up_w) + 2 * x + (q & 1);
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ep.bias) bb = __ldg(reinterpret_cast<const float4*>(ep.bias + co));
+                *reinterpret_cast<float4*>(obase + orow * ep.up_cout + co) =
+                    make_float4(v[g * 4] + bb.x, v[g * 4 + 1] + bb.y, v[g * 4 + 2] + bb.z, v[g * 4 + 3] + bb.w);
+            }
+        }
+    } else if (MODE == PB200_EPI_NCHW_F32) {
+        if (!row_ok) return;
+        const int hw = ep.rows_per_sample;
+        const int b = row / hw, p = row - b * hw;
+        float* o = reinterpret_cast<float*>(ep.out) + ((int64_t)b * N + col0) * hw + p;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) o[(int64_t)j * hw] = v[j];
+    }
+}
+
+// ------------------------------------------------------------------ kernel
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                const pb200_gemm_epilogue ep, int M, int N, int K) {
+    using L = GemmSmem<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + L::STAGES * L::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (L::STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * L::STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * L::STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * L::STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int n_tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+    const int n_tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * n_tiles_n;
+    const int n_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_a);
+        ptx::prefetch_tensormap(&tm_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < L::STAGES; ++s) {
+                ptx::mbar_init(full_bar(s), 1);
+                ptx::mbar_init(empty_bar(s), 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                ptx::mbar_init(tfull_bar(s), 1);
+                ptx::mbar_init(tempty_bar(s), 4);       // one arrival per epilogue warp
+            }
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, L::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m_idx = (tile / n_tiles_n) * GEMM_BLOCK_M;
+                const int n_idx = (tile % n_tiles_n) * BLOCK_N;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+                    ptx::tma_load_2d(&tm_a, full_bar(stage), sa, kb * GEMM_BLOCK_K, m_idx);
+                    ptx::tma_load_2d(&tm_b, full_bar(stage), sa + L::A_BYTES, kb * GEMM_BLOCK_K, n_idx);
+                    if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = ptx::umma_idesc_f16(GEMM_BLOCK_M, BLOCK_N, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            ptx::mbar_wait(tempty_bar(as), aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                ptx::mbar_wait(full_bar(stage), phase);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+                    const uint64_t da = ptx::umma_desc_kmajor_sw128(sa);
+                    const uint64_t db = ptx::umma_desc_kmajor_sw128(sa + L::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+                        // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in (addr>>4)
+                        ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs retire
+                    if (kb == n_kb - 1) ptx::umma_commit(tfull_bar(as)); // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            const int m_idx = (tile / n_tiles_n) * GEMM_BLOCK_M;
+            const int n_idx = (tile % n_tiles_n) * BLOCK_N;
+            ptx::mbar_wait(tfull_bar(as), aphase);
+            ptx::tc_fence_after();
+            const int row = m_idx + q * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                if (n_idx + c >= N) break;
+                float v[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c), v);
+                epilogue_chunk<MODE>(ep, M, N, row, n_idx + c, v, lane);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, L::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ dispatch
+template <int BLOCK_N, int MODE>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_gemm_epilogue& ep, int M, int N, int K,
+                      cudaStream_t st) {
+    using L = GemmSmem<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     L::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int n_tiles = ceil_div(M, GEMM_BLOCK_M) * ceil_div(N, BLOCK_N);
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    gemm_f16_kernel<BLOCK_N, MODE><<<grid, GEMM_THREADS, L::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int BLOCK_N>
+static int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_gemm_epilogue& ep, int M, int N, int K,
+                       cudaStream_t st) {
+    switch (ep.mode) {
+        case PB200_EPI_F16: return launch_cfg<BLOCK_N, PB200_EPI_F16>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_F32: return launch_cfg<BLOCK_N, PB200_EPI_F32>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_GELU_F16: return launch_cfg<BLOCK_N, PB200_EPI_GELU_F16>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_RESID_F32: return launch_cfg<BLOCK_N, PB200_EPI_RESID_F32>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_UNPATCH_F32: return launch_cfg<BLOCK_N, PB200_EPI_UNPATCH_F32>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_NCHW_F32: return launch_cfg<BLOCK_N, PB200_EPI_NCHW_F32>(ta, tb, ep, M, N, K, st);
+    }
+    PB_CHECK(false, "gemm: unknown epilogue mode %d", ep.mode);
+    return 1;
+}
+
+int gemm_pick_block_n(int64_t M, int64_t N) {
+    // minimise (waves x tile cost); tile cost ~ BLOCK_N plus a fixed per-tile overhead
+    const int cands[3] = {256, 128, 64};
+    int best = 128;
+    double best_cost = 1e30;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    for (int i = 0; i < 3; ++i) {
+        const int bn = cands[i];
+        const long tiles = (long)ceil_div(M, GEMM_BLOCK_M) * ceil_div(N, bn);
+        const long waves = (tiles + sms - 1) / sms;
+        const double cost = (double)waves * (bn + 24);
+        if (cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const pb200_gemm_epilogue& ep, int64_t M,
+                int64_t N, int64_t K, cudaStream_t st) {
+    PB_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem");
+    PB_CHECK(N % 8 == 0, "gemm: N=%lld must be a multiple of 8", (long long)N);
+    PB_CHECK(ep.out != nullptr, "gemm: null output");
+    if (ep.mode == PB200_EPI_RESID_F32) PB_CHECK(ep.resid != nullptr, "gemm: RESID epilogue without resid");
+    if (ep.mode == PB200_EPI_UNPATCH_F32)
+        PB_CHECK(ep.up_cout % 8 == 0 && ep.up_cout * 4 == N && (int64_t)ep.up_h * ep.up_w > 0,
+                 "gemm: bad un-patchify geometry");
+    if ((ep.mode == PB200_EPI_GELU_F16 && ep.sqsum) || (ep.mode == PB200_EPI_RESID_F32 && ep.film) ||
+        ep.mode == PB200_EPI_NCHW_F32)
+        PB_CHECK(ep.rows_per_sample > 0, "gemm: rows_per_sample required");
+    switch (block_n) {
+        case 64: return launch_mode<64>(ta, tb, ep, (int)M, (int)N, (int)K, st);
+        case 128: return launch_mode<128>(ta, tb, ep, (int)M, (int)N, (int)K, st);
+        case 256: return launch_mode<256>(ta, tb, ep, (int)M, (int)N, (int)K, st);
+    }
+    PB_CHECK(false, "gemm: unsupported BLOCK_N %d", block_n);
+    return 1;
+}
+
+int gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int64_t N, int64_t K,
+             const pb200_gemm_epilogue& ep, cudaStream_t st) {
+    PB_CHECK(K % 8 == 0, "gemm: K=%lld must be a multiple of 8", (long long)K);
+    const int bn = gemm_pick_block_n(M, N);
+    CUtensorMap ta, tb;
+    PB_TRY(make_tmap_f16_2d(&ta, a, M, K, lda, GEMM_BLOCK_M));
+    PB_TRY(make_tmap_f16_2d(&tb, w, N, K, ldw, bn));
+    return gemm_launch(ta, tb, bn, ep, M, N, K, st);
+}
+
+}  // namespace pb
+
+extern "C" int pb200_gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t m, int64_t n, int64_t k,
+                              const pb200_gemm_epilogue* epi, void* stream) {
+    PB_CHECK(epi != nullptr, "gemm: null epilogue");
+    return pb::gemm_f16(a, lda, w, ldw, m, n, k, *epi, (cudaStream_t)stream);
+}

@@ -1,0 +1,36 @@
+// Internal interface of the tcgen05 GEMM (see gemm.cu).
+#pragma once
+#include "common.cuh"
+#include "paella_b200.h"
+#include "ptx.cuh"
+
+namespace pb {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;     // 64 fp16 = one 128-byte swizzle row
+constexpr int GEMM_THREADS = 192;    // TMA warp, MMA warp, 4 epilogue warps
+
+template <int BLOCK_N>
+struct GemmSmem {
+    static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = BLOCK_N >= 256 ? 512 : (BLOCK_N >= 128 ? 256 : 128);   // 2 accumulators
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+// 2-D fp16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements):
+// box = 64 columns x box_rows rows, 128-byte swizzle, zero fill out of bounds.
+int make_tmap_f16_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
+int gemm_pick_block_n(int64_t M, int64_t N);
+
+int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const pb200_gemm_epilogue& ep, int64_t M,
+                int64_t N, int64_t K, cudaStream_t st);
+
+// convenience: builds both tensor maps and launches
+int gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int64_t N, int64_t K,
+             const pb200_gemm_epilogue& ep, cudaStream_t st);
+
+}  // namespace pb
