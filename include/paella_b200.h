@@ -85,13 +85,13 @@ enum pb200_epilogue {
     PB200_EPI_F32 = 1,        /* out fp32 [M,ldo]   = acc + bias                                        */
     PB200_EPI_GELU_F16 = 2,   /* out fp16 = gelu_erf(acc + bias); sqsum[row/rows_per_sample, n] += out^2 */
     PB200_EPI_RESID_F32 = 3,  /* out fp32 = ((acc + bias)*alpha + resid) [* (1+film_a) + film_b]         */
-    PB200_EPI_UNPATCH_F32 = 4,/* out fp32 NHWC [B,2h,2w,cout]: col=(dy,dx,co), row=(b,y,x); bias[co]     */
+    PB200_EPI_UNPATCH_F32 = 4,/* out fp32 NHWC [B,2h,2w,cout]: col=(dy,dx,co), row=(b,y,x); bias[col]    */
     PB200_EPI_NCHW_F32 = 5    /* out fp32 [B, N, hw]: row=(b,p) -> out[b][n][p]; acc + bias              */
 };
 
 typedef struct pb200_gemm_epilogue {
     int mode;                  /* enum pb200_epilogue */
-    const float* bias;         /* [N] (UNPATCH: [cout]) or NULL */
+    const float* bias;         /* [N] or NULL */
     void* out;
     int64_t ldo;               /* leading dimension of out in elements (F16/F32/GELU/RESID) */
     const float* resid;        /* RESID: fp32 [M, ldr] (may alias out) */

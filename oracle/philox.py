@@ -97,8 +97,9 @@ def rand(numel: int, seed: int, offset: int, sm_count: int) -> np.ndarray:
 
 
 def exponential(numel: int, seed: int, offset: int, sm_count: int) -> np.ndarray:
-    """Tensor.exponential_(1) fp32 on CUDA.  NB: CPU ``np.log`` may differ from the
-    device ``logf`` by an ulp; bit-exact checks of this transform are done on the GPU."""
+    """Tensor.exponential_(1) fp32 on CUDA.  NB: the device uses the fast ``__logf``
+    (ATen/NumericUtils.h:149-160: lg2.approx * ln2), which no CPU log reproduces bit for bit;
+    bit-exact checks of this transform are done on the GPU against torch itself."""
     u = u32_to_uniform(raw_u32(numel, seed, offset, sm_count))
     eps = np.finfo(np.float32).eps
     lg = np.where(u >= np.float32(1.0) - eps / 2, np.float32(-eps / 2), np.log(u).astype(np.float32))

@@ -1,0 +1,22 @@
+// Attention core (see attention.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+struct AttnParams {
+    const __half* qkv;     // [B*P, 3E]: q | k_self | v_self
+    const __half* ckv;     // [B, S_max, 2E]: k_cond | v_cond
+    const int* kv_len;     // [B] valid conditioning rows per sample (NULL: S_max)
+    __half* out;           // [B*P, E]
+    int B, P, S_max, E, nhead;
+    int self_attn;         // keys = [self ; cond] (1) or cond only (0)
+    float scale_log2;      // log2(e) / sqrt(head_dim)
+    const float* attn_w;   // optional post-softmax weights for the last n_w keys ...
+    int n_w;
+    int w_batch;           // ... of samples [0, w_batch)
+};
+
+int launch_attention(const AttnParams& p, cudaStream_t st);
+
+}  // namespace pb

@@ -60,8 +60,8 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, int M, int N, int row, int col0,
                                                float (&v)[32], int lane) {
     const bool row_ok = row < M;
-    // ---- bias
-    if (MODE != PB200_EPI_UNPATCH_F32) {
+    // ---- bias (indexed by GEMM column in every mode)
+    {
         if (ep.bias) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
@@ -176,10 +176,8 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
             if (col < N) {
                 const int q = col / ep.up_cout, co = col - q * ep.up_cout;    // q = dy*2+dx
                 const int64_t orow = ((int64_t)b * 2 * ep.up_h + 2 * y + (q >> 1)) * (2 * ep.up_w) + 2 * x + (q & 1);
-                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ep.bias) bb = __ldg(reinterpret_cast<const float4*>(ep.bias + co));
                 *reinterpret_cast<float4*>(obase + orow * ep.up_cout + co) =
-                    make_float4(v[g * 4] + bb.x, v[g * 4 + 1] + bb.y, v[g * 4 + 2] + bb.z, v[g * 4 + 3] + bb.w);
+                    make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
             }
         }
     } else if (MODE == PB200_EPI_NCHW_F32) {

@@ -1,0 +1,465 @@
+// Memory-bound kernels of the denoiser (all channels-last, fp32 residual stream, fp16 GEMM operands).
+//   embed_tokens   in_mapper (Embedding + LayerNorm) + PixelUnshuffle      ref/src/modules.py:126-131,271
+//   ln_rows        LayerNorm2d / nn.LayerNorm(no affine, eps 1e-6)         ref/src/modules.py:22-27,125
+//   ln_patchify2   LayerNorm2d + the im2col of Conv2d(k=2,s=2)             ref/src/modules.py:153-156
+//   dwconv_ln      ResBlock.depthwise (+cat skip, groups=c) + LayerNorm2d  ref/src/modules.py:46-47,57-60
+//   grn_*          GlobalResponseNorm                                      ref/src/modules.py:30-40
+//   r_embed / film gen_r_embedding + TimestepBlock.mapper                  ref/src/modules.py:212-221,99-106
+//   silu_cast      AttnBlock.kv_mapper's SiLU                              ref/src/modules.py:71-74
+#include "ops.cuh"
+
+namespace pb {
+
+constexpr float LN_EPS = 1e-6f;
+
+__device__ __forceinline__ float ln_rstd(float var) { return 1.0f / sqrtf(var + LN_EPS); }
+
+// ------------------------------------------------------------------ embed_tokens
+// one warp per output row (b, y2, x2); row staged in shared memory so the global store is contiguous
+__global__ void __launch_bounds__(256) embed_tokens_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ emb,
+                                                           int num_labels, int c_in, int B, int H, int W, int ps,
+                                                           __half* __restrict__ out) {
+    extern __shared__ __half s_row[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h2 = H / ps, w2 = W / ps;
+    const int64_t orow = (int64_t)blockIdx.x * 8 + warp;
+    const int rowlen = c_in * ps * ps;
+    __half* srow = s_row + warp * rowlen;
+    if (orow < (int64_t)B * h2 * w2) {
+        const int b = (int)(orow / (h2 * w2));
+        const int rem = (int)(orow - (int64_t)b * h2 * w2);
+        const int y2 = rem / w2, x2 = rem - y2 * w2;
+        for (int dy = 0; dy < ps; ++dy)
+            for (int dx = 0; dx < ps; ++dx) {
+                int64_t tok = tokens[((int64_t)b * H + y2 * ps + dy) * W + x2 * ps + dx];
+                tok = tok < 0 ? 0 : (tok >= num_labels ? num_labels - 1 : tok);
+                const float* e = emb + tok * c_in;
+                float s = 0.f;
+                for (int c = lane; c < c_in; c += 32) s += e[c];
+                const float mean = warp_sum(s) / c_in;
+                float v = 0.f;
+                for (int c = lane; c < c_in; c += 32) { const float d = e[c] - mean; v = fmaf(d, d, v); }
+                const float rstd = ln_rstd(warp_sum(v) / c_in);
+                for (int c = lane; c < c_in; c += 32) srow[c * ps * ps + dy * ps + dx] = __float2half_rn((e[c] - mean) * rstd);
+            }
+    }
+    __syncwarp();
+    if (orow < (int64_t)B * h2 * w2) {
+        __half* o = out + orow * rowlen;
+        if ((rowlen & 7) == 0) {
+            for (int i = lane * 8; i < rowlen; i += 256) *reinterpret_cast<uint4*>(o + i) = *reinterpret_cast<const uint4*>(srow + i);
+        } else {
+            for (int i = lane; i < rowlen; i += 32) o[i] = srow[i];
+        }
+    }
+}
+
+int launch_embed_tokens(const int64_t* tokens, const float* emb, int num_labels, int c_in, int B, int H, int W, int ps,
+                        __half* out, cudaStream_t st) {
+    PB_CHECK(H % ps == 0 && W % ps == 0, "embed: latent %dx%d not divisible by patch_size %d", H, W, ps);
+    const int64_t rows = (int64_t)B * (H / ps) * (W / ps);
+    const size_t smem = (size_t)8 * c_in * ps * ps * sizeof(__half);
+    PB_CHECK(smem <= 48 * 1024, "embed: c_in*patch^2 too large");
+    embed_tokens_kernel<<<ceil_div(rows, 8), 256, smem, st>>>(tokens, emb, num_labels, c_in, B, H, W, ps, out);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ LayerNorm over rows (warp per row)
+template <bool PATCHIFY>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, int64_t rows, int C, float scale,
+                                                      float shift, __half* __restrict__ out16, float* __restrict__ out32,
+                                                      int h, int w) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+    const int nv = C >> 2;
+    float s = 0.f;
+    for (int i = lane; i < nv; i += 32) { const float4 v = xr[i]; s += (v.x + v.y) + (v.z + v.w); }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+        const float4 v = xr[i];
+        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = ln_rstd(warp_sum(q) / C) * scale;
+    int64_t obase = row * C;
+    if (PATCHIFY) {   // row = (b, y, x) on an h x w grid -> out row (b, y/2, x/2), column block (y%2*2 + x%2)
+        const int64_t hw = (int64_t)h * w;
+        const int64_t b = row / hw;
+        const int rem = (int)(row - b * hw);
+        const int y = rem / w, xx = rem - y * w;
+        obase = ((b * (h >> 1) + (y >> 1)) * (w >> 1) + (xx >> 1)) * (4 * (int64_t)C) + ((y & 1) * 2 + (xx & 1)) * C;
+    }
+    for (int i = lane; i < nv; i += 32) {
+        const float4 v = xr[i];
+        const float a = fmaf(v.x - mean, rstd, shift), b = fmaf(v.y - mean, rstd, shift);
+        const float c = fmaf(v.z - mean, rstd, shift), d = fmaf(v.w - mean, rstd, shift);
+        if (out16) {
+            uint2 pk;
+            pk.x = pack_half2(a, b);
+            pk.y = pack_half2(c, d);
+            *reinterpret_cast<uint2*>(out16 + obase + i * 4) = pk;
+        } else {
+            *reinterpret_cast<float4*>(out32 + obase + i * 4) = make_float4(a, b, c, d);
+        }
+    }
+}
+
+int launch_ln_rows(const float* x, int64_t rows, int C, float scale, float shift, __half* out16, float* out32,
+                   cudaStream_t st) {
+    PB_CHECK(C % 4 == 0, "layernorm: C=%d must be a multiple of 4", C);
+    PB_CHECK((out16 != nullptr) != (out32 != nullptr), "layernorm: exactly one output");
+    if (rows == 0) return 0;
+    ln_rows_kernel<false><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, C, scale, shift, out16, out32, 0, 0);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_ln_patchify2(const float* x, int B, int h, int w, int c, __half* out, cudaStream_t st) {
+    PB_CHECK(c % 4 == 0 && h % 2 == 0 && w % 2 == 0, "ln_patchify: bad geometry %dx%dx%d", h, w, c);
+    const int64_t rows = (int64_t)B * h * w;
+    ln_rows_kernel<true><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, c, 1.0f, 0.0f, out, nullptr, h, w);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ depthwise conv + LayerNorm (warp per position)
+// NV = float4 chunks per lane: supports c <= NV*128.
+template <int NV, bool SKIP>
+__global__ void __launch_bounds__(128) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ skip,
+                                                        const float* __restrict__ wp, const float* __restrict__ bias,
+                                                        int B, int h, int w, int c, int k, __half* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t pos = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (pos >= (int64_t)B * h * w) return;
+    const int b = (int)(pos / ((int64_t)h * w));
+    const int rem = (int)(pos - (int64_t)b * h * w);
+    const int y = rem / w, xx = rem - y * w;
+    const int nvq = c >> 2;          // float4 chunks in a row
+    const int pad = k >> 1;
+    float4 acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int q = i * 32 + lane;
+        acc[i] = q < nvq ? __ldg(reinterpret_cast<const float4*>(bias) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int ky = 0; ky < k; ++ky) {
+        const int iy = y + ky - pad;
+        if (iy < 0 || iy >= h) continue;
+        for (int kx = 0; kx < k; ++kx) {
+            const int ix = xx + kx - pad;
+            if (ix < 0 || ix >= w) continue;
+            const int64_t ipos = ((int64_t)b * h + iy) * w + ix;
+            const int tap = ky * k + kx;
+            if (!SKIP) {
+                const float4* xr = reinterpret_cast<const float4*>(x + ipos * c);
+                const float4* wr = reinterpret_cast<const float4*>(wp + (int64_t)tap * c);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const int q = i * 32 + lane;
+                    if (q < nvq) {
+                        const float4 v = xr[q], ww = __ldg(wr + q);
+                        acc[i].x = fmaf(v.x, ww.x, acc[i].x); acc[i].y = fmaf(v.y, ww.y, acc[i].y);
+                        acc[i].z = fmaf(v.z, ww.z, acc[i].z); acc[i].w = fmaf(v.w, ww.w, acc[i].w);
+                    }
+                }
+            } else {
+                // output channels g = 4q..4q+3 read concatenated [x, skip] channels 8q..8q+7
+                const float4* w0 = reinterpret_cast<const float4*>(wp + ((int64_t)tap * 2 + 0) * c);
+                const float4* w1 = reinterpret_cast<const float4*>(wp + ((int64_t)tap * 2 + 1) * c);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const int q = i * 32 + lane;
+                    if (q < nvq) {
+                        const int cc = 8 * q;
+                        const float* src = cc < c ? x + ipos * c + cc : skip + ipos * c + (cc - c);
+                        const float4 lo = *reinterpret_cast<const float4*>(src);
+                        const float4 hi = *reinterpret_cast<const float4*>(src + 4);
+                        const float4 a = __ldg(w0 + q), bb = __ldg(w1 + q);
+                        acc[i].x = fmaf(lo.x, a.x, fmaf(lo.y, bb.x, acc[i].x));
+                        acc[i].y = fmaf(lo.z, a.y, fmaf(lo.w, bb.y, acc[i].y));
+                        acc[i].z = fmaf(hi.x, a.z, fmaf(hi.y, bb.z, acc[i].z));
+                        acc[i].w = fmaf(hi.z, a.w, fmaf(hi.w, bb.w, acc[i].w));
+                    }
+                }
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (i * 32 + lane < nvq) s += (acc[i].x + acc[i].y) + (acc[i].z + acc[i].w);
+    const float mean = warp_sum(s) / c;
+    float qv = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (i * 32 + lane < nvq) {
+            const float a = acc[i].x - mean, bq = acc[i].y - mean, cq = acc[i].z - mean, d = acc[i].w - mean;
+            qv += (a * a + bq * bq) + (cq * cq + d * d);
+        }
+    const float rstd = ln_rstd(warp_sum(qv) / c);
+    __half* o = out + pos * c;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int q = i * 32 + lane;
+        if (q < nvq) {
+            uint2 pk;
+            pk.x = pack_half2((acc[i].x - mean) * rstd, (acc[i].y - mean) * rstd);
+            pk.y = pack_half2((acc[i].z - mean) * rstd, (acc[i].w - mean) * rstd);
+            *reinterpret_cast<uint2*>(o + q * 4) = pk;
+        }
+    }
+}
+
+template <int NV>
+static int dwconv_dispatch(const float* x, const float* skip, const float* wp, const float* bias, int B, int h, int w,
+                           int c, int k, __half* out, cudaStream_t st) {
+    const int64_t npos = (int64_t)B * h * w;
+    if (skip)
+        dwconv_ln_kernel<NV, true><<<ceil_div(npos, 4), 128, 0, st>>>(x, skip, wp, bias, B, h, w, c, k, out);
+    else
+        dwconv_ln_kernel<NV, false><<<ceil_div(npos, 4), 128, 0, st>>>(x, skip, wp, bias, B, h, w, c, k, out);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_dwconv_ln(const float* x, const float* skip, const float* w_packed, const float* bias, int B, int h, int w,
+                     int c, int k, __half* out, cudaStream_t st) {
+    PB_CHECK(c % 8 == 0, "dwconv: c=%d must be a multiple of 8", c);
+    PB_CHECK(k % 2 == 1, "dwconv: kernel_size %d must be odd", k);
+    if (c <= 128) return dwconv_dispatch<1>(x, skip, w_packed, bias, B, h, w, c, k, out, st);
+    if (c <= 640) return dwconv_dispatch<5>(x, skip, w_packed, bias, B, h, w, c, k, out, st);
+    if (c <= 1280) return dwconv_dispatch<10>(x, skip, w_packed, bias, B, h, w, c, k, out, st);
+    if (c <= 2560) return dwconv_dispatch<20>(x, skip, w_packed, bias, B, h, w, c, k, out, st);
+    PB_CHECK(false, "dwconv: c=%d > 2560 unsupported", c);
+    return 1;
+}
+
+// ------------------------------------------------------------------ GlobalResponseNorm
+__global__ void __launch_bounds__(256) grn_scale_kernel(float* __restrict__ sqsum, const float* __restrict__ gamma, int N,
+                                                        float* __restrict__ scale) {
+    const int b = blockIdx.x;
+    float* sq = sqsum + (int64_t)b * N;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s += sqrtf(sq[i]);
+    __shared__ float red[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float denom = tot / N + 1e-6f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float gx = sqrtf(sq[i]);
+        scale[(int64_t)b * N + i] = fmaf(gamma[i], gx / denom, 1.0f);
+        sq[i] = 0.f;          // ready for the next ResBlock's GEMM epilogue
+    }
+}
+
+__global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ h, int64_t M, int N, int P,
+                                                        const float* __restrict__ scale, const float* __restrict__ beta) {
+    const int nv = N >> 3;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * nv) return;
+    const int64_t row = i / nv;
+    const int col = (int)(i - row * nv) * 8;
+    const float* sc = scale + (row / P) * N + col;
+    uint4 v = *reinterpret_cast<uint4*>(h + row * N + col);
+    __half2* hv = reinterpret_cast<__half2*>(&v);
+    const float4 s0 = *reinterpret_cast<const float4*>(sc), s1 = *reinterpret_cast<const float4*>(sc + 4);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    float2 f;
+    f = __half22float2(hv[0]); hv[0] = __floats2half2_rn(fmaf(f.x, s0.x, b0.x), fmaf(f.y, s0.y, b0.y));
+    f = __half22float2(hv[1]); hv[1] = __floats2half2_rn(fmaf(f.x, s0.z, b0.z), fmaf(f.y, s0.w, b0.w));
+    f = __half22float2(hv[2]); hv[2] = __floats2half2_rn(fmaf(f.x, s1.x, b1.x), fmaf(f.y, s1.y, b1.y));
+    f = __half22float2(hv[3]); hv[3] = __floats2half2_rn(fmaf(f.x, s1.z, b1.z), fmaf(f.y, s1.w, b1.w));
+    *reinterpret_cast<uint4*>(h + row * N + col) = v;
+}
+
+int launch_grn_scale(float* sqsum, const float* gamma, int B, int N, float* scale, cudaStream_t st) {
+    grn_scale_kernel<<<B, 256, 0, st>>>(sqsum, gamma, N, scale);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_grn_apply(__half* h, int64_t M, int N, int P, const float* scale, const float* beta, cudaStream_t st) {
+    PB_CHECK(N % 8 == 0, "grn: N=%d must be a multiple of 8", N);
+    grn_apply_kernel<<<ceil_div(M * (N / 8), 256), 256, 0, st>>>(h, M, N, P, scale, beta);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ timestep embedding + FiLM table
+__global__ void r_embed_kernel(const float* __restrict__ r, int B, int c_r, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * c_r) return;
+    const int b = i / c_r, j = i - b * c_r;
+    const int half = c_r / 2;
+    if (j >= 2 * half) { out[i] = 0.f; return; }          // odd c_r: zero pad
+    const int f = j < half ? j : j - half;
+    const float kneg = (float)(-(log(10000.0) / (double)(half - 1)));
+    const float freq = expf(__fmul_rn((float)f, kneg));
+    const float ang = __fmul_rn(__fmul_rn(r[b], 10000.0f), freq);
+    out[i] = j < half ? sinf(ang) : cosf(ang);
+}
+
+int launch_r_embed(const float* r, int B, int c_r, float* out, cudaStream_t st) {
+    PB_CHECK(c_r >= 4, "c_r=%d too small", c_r);
+    r_embed_kernel<<<ceil_div((long)B * c_r, 128), 128, 0, st>>>(r, B, c_r, out);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+// thread = one output feature j, its W row in registers; loops over the batch (r_embed staged in shared memory)
+template <int CR>
+__global__ void __launch_bounds__(128) film_table_kernel(const float* __restrict__ r_embed, int B, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, int total, float* __restrict__ out) {
+    extern __shared__ float s_r[];           // [bt, CR]
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    float wr[CR];
+    if (j < total) {
+#pragma unroll
+        for (int i = 0; i < CR; i += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)j * CR + i));
+            wr[i] = v.x; wr[i + 1] = v.y; wr[i + 2] = v.z; wr[i + 3] = v.w;
+        }
+    }
+    const float bj = j < total ? bias[j] : 0.f;
+    for (int b0 = 0; b0 < B; b0 += 64) {
+        const int bt = min(64, B - b0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < bt * CR; i += 128) s_r[i] = r_embed[(int64_t)b0 * CR + i];
+        __syncthreads();
+        if (j < total) {
+            for (int b = 0; b < bt; ++b) {
+                float acc = bj;
+#pragma unroll
+                for (int i = 0; i < CR; ++i) acc = fmaf(s_r[b * CR + i], wr[i], acc);
+                out[(int64_t)(b0 + b) * total + j] = acc;
+            }
+        }
+    }
+}
+
+__global__ void film_table_generic_kernel(const float* __restrict__ r_embed, int B, int c_r, const float* __restrict__ W,
+                                          const float* __restrict__ bias, int total, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * total) return;
+    const int b = (int)(i / total), j = (int)(i - (int64_t)b * total);
+    float acc = bias[j];
+    for (int k = 0; k < c_r; ++k) acc = fmaf(r_embed[b * c_r + k], W[(int64_t)j * c_r + k], acc);
+    out[i] = acc;
+}
+
+int launch_film_table(const float* r_embed, int B, int c_r, const float* W, const float* bias, int total, float* out,
+                      cudaStream_t st) {
+    if (total == 0) return 0;
+    if (c_r == 64)
+        film_table_kernel<64><<<ceil_div(total, 128), 128, 64 * 64 * sizeof(float), st>>>(r_embed, B, W, bias, total, out);
+    else
+        film_table_generic_kernel<<<ceil_div((long)B * total, 256), 256, 0, st>>>(r_embed, B, c_r, W, bias, total, out);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void film_apply_kernel(float* __restrict__ x, int64_t M, int N, int P, const float* __restrict__ film,
+                                  int64_t film_ld, int64_t film_off) {
+    const int nv = N >> 2;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * nv) return;
+    const int64_t row = i / nv;
+    const int col = (int)(i - row * nv) * 4;
+    const float* fa = film + (row / P) * film_ld + film_off + col;
+    float4 v = *reinterpret_cast<float4*>(x + row * N + col);
+    const float4 a = *reinterpret_cast<const float4*>(fa), s = *reinterpret_cast<const float4*>(fa + N);
+    v.x = fmaf(v.x, 1.0f + a.x, s.x); v.y = fmaf(v.y, 1.0f + a.y, s.y);
+    v.z = fmaf(v.z, 1.0f + a.z, s.z); v.w = fmaf(v.w, 1.0f + a.w, s.w);
+    *reinterpret_cast<float4*>(x + row * N + col) = v;
+}
+
+int launch_film_apply(float* x, int64_t M, int N, int P, const float* film, int64_t film_ld, int64_t film_off,
+                      cudaStream_t st) {
+    PB_CHECK(N % 4 == 0 && film_off % 4 == 0 && film_ld % 4 == 0, "film: misaligned table");
+    film_apply_kernel<<<ceil_div(M * (N / 4), 256), 256, 0, st>>>(x, M, N, P, film, film_ld, film_off);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ casts
+template <int OP>
+__global__ void cast_kernel(const float* __restrict__ a, const float* __restrict__ b, float wa, float wb, int64_t n,
+                            __half* __restrict__ out) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float t = (i + j < n) ? a[i + j] : 0.f;
+        if (OP == 1) t = t / (1.0f + expf(-t));                                   // SiLU
+        if (OP == 2) t = b ? fmaf(t, wa, b[(i + j < n) ? i + j : 0] * wb) : t * wa;  // weighted mix
+        v[j] = t;
+    }
+    if (i + 3 < n && ((reinterpret_cast<uintptr_t>(out + i) & 7) == 0)) {
+        uint2 pk;
+        pk.x = pack_half2(v[0], v[1]);
+        pk.y = pack_half2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(out + i) = pk;
+    } else {
+        for (int j = 0; j < 4 && i + j < n; ++j) out[i + j] = __float2half_rn(v[j]);
+    }
+}
+
+int launch_cast_f16(const float* x, int64_t n, __half* out, cudaStream_t st) {
+    if (n == 0) return 0;
+    cast_kernel<0><<<ceil_div(ceil_div(n, 4), 256), 256, 0, st>>>(x, nullptr, 1.f, 0.f, n, out);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+int launch_silu_cast_f16(const float* x, int64_t n, __half* out, cudaStream_t st) {
+    if (n == 0) return 0;
+    cast_kernel<1><<<ceil_div(ceil_div(n, 4), 256), 256, 0, st>>>(x, nullptr, 1.f, 0.f, n, out);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+int launch_mix_cast_f16(const float* a, const float* b, float wa, float wb, int64_t n, __half* out, cudaStream_t st) {
+    if (n == 0) return 0;
+    cast_kernel<2><<<ceil_div(ceil_div(n, 4), 256), 256, 0, st>>>(a, b, wa, wb, n, out);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ layout
+// [B, R, Cc] -> [B, Cc, R] through a 32x33 shared tile
+__global__ void transpose_kernel(const float* __restrict__ in, int R, int Cc, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const float* src = in + (int64_t)b * R * Cc;
+    float* dst = out + (int64_t)b * R * Cc;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < R && c < Cc) tile[i][threadIdx.x] = src[(int64_t)r * Cc + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < Cc) dst[(int64_t)c * R + r] = tile[threadIdx.x][i];
+    }
+}
+
+static int transpose(const float* in, int B, int R, int Cc, float* out, cudaStream_t st) {
+    if (B == 0 || R == 0 || Cc == 0) return 0;
+    dim3 grid(ceil_div(Cc, 32), ceil_div(R, 32), B), block(32, 8);
+    PB_CHECK(grid.y <= 65535 && grid.z <= 65535, "transpose: grid too large");
+    transpose_kernel<<<grid, block, 0, st>>>(in, R, Cc, out);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_nchw_to_nhwc(const float* in, int B, int C, int HW, float* out, cudaStream_t st) { return transpose(in, B, C, HW, out, st); }
+int launch_nhwc_to_nchw(const float* in, int B, int C, int HW, float* out, cudaStream_t st) { return transpose(in, B, HW, C, out, st); }
+
+}  // namespace pb

@@ -1,0 +1,185 @@
+// Fused out_mapper GEMM + temperature + multinomial draw: logits never reach HBM.
+// Replaces ref/src/modules.py:184-187 (out_mapper 1x1 conv, 256 -> 8192) and ref/src/utils.py:45-50
+// (CFG mix, /T, softmax, permute+reshape copy, torch.multinomial) — ~0.74 GB of HBM traffic per image-step in
+// the reference, ~1 MB here.
+//
+// The classifier-free-guidance mix is linear, so it is applied to the 256-wide LayerNorm'd features BEFORE the
+// GEMM (one GEMM instead of two).  The draw is Gumbel-max in the log domain on torch's own random stream:
+//     token = argmax_k ( l_k / T  -  log q_k ),   q_k = the Exp(1) variate torch.multinomial's
+//                                                  exponential_() would hand to element (row, k)
+// which equals argmax_k softmax(l/T)_k / q_k (what torch computes) up to fp32 rounding of near-ties.
+//
+// One CTA per 128 token rows, 320 threads:
+//   warp 0     TMA: the 128 x c_out A tile once (resident), then W tiles [128 labels x 64] through a 6-deep ring
+//   warp 1     tcgen05.mma issuer: 128x128 accumulators, double-buffered in TMEM
+//   warps 2-9  epilogue: tcgen05.ld (thread = token row), Philox4x32-10 per element, running arg-max in registers
+#include "gemm.cuh"
+#include "sampler.cuh"
+
+namespace pb {
+
+constexpr int SMP_BN = 128;
+constexpr int SMP_STAGES = 6;
+constexpr int SMP_MAX_KB = 4;                 // c_out <= 256
+constexpr int SMP_THREADS = 320;
+constexpr int SMP_A_BYTES = 128 * 64 * 2;     // one k-block of the A tile
+constexpr int SMP_W_BYTES = SMP_BN * 64 * 2;
+constexpr int SMP_SMEM = SMP_MAX_KB * SMP_A_BYTES + SMP_STAGES * SMP_W_BYTES + 1024 + 256 + 2 * 128 * 8;
+
+__global__ void __launch_bounds__(SMP_THREADS, 1)
+fused_sampler_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, int R, int NL,
+                     int Kc, float inv_t, TorchPhilox rng, int64_t* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t a_base = smem_base;
+    const uint32_t w_base = smem_base + SMP_MAX_KB * SMP_A_BYTES;
+    const uint32_t bar_base = w_base + SMP_STAGES * SMP_W_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (SMP_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * SMP_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * SMP_STAGES + 2 + s); };
+    const uint32_t a_bar = bar_base + 8u * (2 * SMP_STAGES + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * SMP_STAGES + 5);
+    uint8_t* tail = smem_gen + (bar_base - smem_base) + 256;
+    float* best_v = reinterpret_cast<float*>(tail);                // [128] second half's candidate
+    int* best_i = reinterpret_cast<int*>(tail + 128 * 4);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int n_kb = (Kc + 63) / 64;
+    const int n_chunks = (NL + SMP_BN - 1) / SMP_BN;
+    const int m_idx = blockIdx.x * 128;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_a);
+        ptx::prefetch_tensormap(&tm_w);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < SMP_STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 8); }
+            ptx::mbar_init(a_bar, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 256);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(a_bar, n_kb * SMP_A_BYTES);
+            for (int kb = 0; kb < n_kb; ++kb) ptx::tma_load_2d(&tm_a, a_bar, a_base + kb * SMP_A_BYTES, kb * 64, m_idx);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ch = 0; ch < n_chunks; ++ch)
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), SMP_W_BYTES);
+                    ptx::tma_load_2d(&tm_w, full_bar(stage), w_base + stage * SMP_W_BYTES, kb * 64, ch * SMP_BN);
+                    if (++stage == SMP_STAGES) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = ptx::umma_idesc_f16(128, SMP_BN, 0);
+        ptx::mbar_wait(a_bar, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int as = ch & 1;
+            ptx::mbar_wait(tempty_bar(as), ((ch >> 1) & 1) ^ 1);
+            ptx::tc_fence_after();
+            for (int kb = 0; kb < n_kb; ++kb) {
+                ptx::mbar_wait(full_bar(stage), phase);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t da = ptx::umma_desc_kmajor_sw128(a_base + kb * SMP_A_BYTES);
+                    const uint64_t db = ptx::umma_desc_kmajor_sw128(w_base + stage * SMP_W_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16(tmem_base + as * SMP_BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(empty_bar(stage));
+                    if (kb == n_kb - 1) ptx::umma_commit(tfull_bar(as));
+                }
+                __syncwarp();
+                if (++stage == SMP_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;                  // TMEM lane quarter
+        const int half = (warp - 2) >> 2;        // which 64 of the chunk's 128 columns
+        const int row_in_tile = q * 32 + lane;
+        const int row = m_idx + row_in_tile;
+        const bool row_ok = row < R;
+        float bv = -INFINITY;
+        int bidx = 0;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int as = ch & 1;
+            ptx::mbar_wait(tfull_bar(as), (ch >> 1) & 1);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 64; c += 32) {
+                const int col0 = ch * SMP_BN + half * 64 + c;
+                float v[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * SMP_BN + half * 64 + c), v);
+                if (row_ok && col0 < NL) {
+                    const uint64_t e0 = (uint64_t)row * (uint64_t)NL + (uint64_t)col0;
+                    uint64_t j = e0 / rng.stride;
+                    uint32_t tid = (uint32_t)(e0 - j * rng.stride);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint4 r4 = torch_philox_call(rng, tid, j >> 2);
+                        const uint32_t ln = (uint32_t)(j & 3);
+                        const uint32_t bits = ln == 0 ? r4.x : ln == 1 ? r4.y : ln == 2 ? r4.z : r4.w;
+                        const float qv = torch_exponential1(u32_to_uniform(bits));
+                        const float gum = fmaf(v[i], inv_t, -__logf(qv));
+                        if (col0 + i < NL && gum > bv) { bv = gum; bidx = col0 + i; }
+                        if (++tid == rng.stride) { tid = 0; ++j; }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+        }
+        // combine the two column halves of each row
+        if (half == 1) { best_v[row_in_tile] = bv; best_i[row_in_tile] = bidx; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0 && row_ok) {
+            const float ov = best_v[row_in_tile];
+            const int oi = best_i[row_in_tile];
+            if (ov > bv || (ov == bv && oi < bidx)) bidx = oi;
+            out[row] = bidx;
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+int launch_fused_sampler(const __half* a16, int64_t R, int Kc, const __half* w16, int NL, float inv_t, uint64_t seed,
+                         uint64_t offset, int64_t* out, cudaStream_t st) {
+    PB_CHECK(Kc % 8 == 0 && Kc <= 64 * SMP_MAX_KB, "fused sampler: c_out=%d unsupported (<= %d, multiple of 8)", Kc, 64 * SMP_MAX_KB);
+    PB_CHECK(R * (int64_t)NL < (1ll << 31), "fused sampler: rows*labels >= 2^31 would split the torch kernel (unsupported)");
+    PB_CHECK(offset % 4 == 0, "philox offset must be a multiple of 4");
+    if (R == 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(fused_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMP_SMEM));
+        attr_set = true;
+    }
+    CUtensorMap ta, tw;
+    PB_TRY(make_tmap_f16_2d(&ta, a16, R, Kc, Kc, 128));
+    PB_TRY(make_tmap_f16_2d(&tw, w16, NL, Kc, Kc, SMP_BN));
+    TorchPhilox rng = make_torch_philox(seed, offset, R * (int64_t)NL);
+    fused_sampler_kernel<<<ceil_div(R, 128), SMP_THREADS, SMP_SMEM, st>>>(ta, tw, (int)R, NL, Kc, inv_t, rng, out);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace pb

@@ -6,20 +6,6 @@
 #define PB_TODO(name) pb::set_error(std::string(name) + ": not implemented yet"); return 1
 
 extern "C" {
-int pb200_paella_create(const pb200_paella_config*, pb200_paella**) { PB_TODO("pb200_paella_create"); }
-void pb200_paella_destroy(pb200_paella*) {}
-int64_t pb200_paella_weight_bytes(const pb200_paella*) { return 0; }
-int pb200_paella_bind_weights(pb200_paella*, void*) { PB_TODO("pb200_paella_bind_weights"); }
-int pb200_paella_num_params(const pb200_paella*) { return 0; }
-const char* pb200_paella_param_name(const pb200_paella*, int) { return ""; }
-int64_t pb200_paella_param_numel(const pb200_paella*, int) { return 0; }
-int pb200_paella_load_param(pb200_paella*, const char*, const float*, int64_t, void*) { PB_TODO("pb200_paella_load_param"); }
-int64_t pb200_paella_workspace_bytes(const pb200_paella*, int, int, int, int) { return 0; }
-int64_t pb200_paella_cond_cache_bytes(const pb200_paella*, int, int) { return 0; }
-int pb200_paella_prepare_cond(pb200_paella*, const pb200_cond*, int, int, int, int, void*, void*, int64_t, void*) { PB_TODO("pb200_paella_prepare_cond"); }
-int pb200_paella_features(pb200_paella*, const int64_t*, const float*, int, int, int, const void*, int, const float*, int, int, float*, void*, int64_t, void*) { PB_TODO("pb200_paella_features"); }
-int pb200_paella_logits(pb200_paella*, const float*, int, int, float*, void*, int64_t, void*) { PB_TODO("pb200_paella_logits"); }
-int pb200_paella_sample_tokens(pb200_paella*, const float*, int, int, int, double, double, uint64_t, uint64_t, int64_t*, void*, int64_t, void*) { PB_TODO("pb200_paella_sample_tokens"); }
 int pb200_vqgan_create(const pb200_vqgan_config*, pb200_vqgan**) { PB_TODO("pb200_vqgan_create"); }
 void pb200_vqgan_destroy(pb200_vqgan*) {}
 int64_t pb200_vqgan_weight_bytes(const pb200_vqgan*) { return 0; }

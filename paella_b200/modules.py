@@ -1,0 +1,403 @@
+"""Python mirror of the reference denoiser's class surface (ref/src/modules.py, ref/utils/modules.py).
+
+Same class names, constructor kwargs, attribute names and state-dict keys as the reference, so
+``load_state_dict(paella_v3.pt)`` and ``paella_inference.ipynb`` work unchanged — but ``forward`` runs the
+hand-written sm_100a kernels behind the C ABI (include/paella_b200.h).  The ``torch.nn`` layers created
+here are PARAMETER HOLDERS ONLY (they give the reference's key names and initialisation); none of their
+``forward`` methods is ever called, and there is no PyTorch or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib, ops
+from ._lib import PaellaB200Error, check, current_stream, lib, ptr
+
+
+# ------------------------------------------------------------------------------------------------
+# Building blocks — parameter layout of ref/src/modules.py:7-106
+# ------------------------------------------------------------------------------------------------
+def _standalone_forward_error(name: str):
+    raise PaellaB200Error(
+        f"{name}.forward outside a Paella model is not wired to the CUDA library yet; "
+        "blocks are executed by Paella.forward's fused plan (no PyTorch fallback exists).")
+
+
+class Attention2D(nn.Module):
+    """ref/src/modules.py:7-19.  ``attn`` holds in_proj_weight/bias and out_proj.* under the reference's keys."""
+
+    def __init__(self, c, nhead, dropout=0.0):
+        super().__init__()
+        self.attn = torch.nn.MultiheadAttention(c, nhead, dropout=dropout, bias=True, batch_first=True)
+
+    def forward(self, x, kv, self_attn=False, **kwargs):
+        _standalone_forward_error("Attention2D")
+
+
+class LayerNorm2d(nn.LayerNorm):
+    """ref/src/modules.py:22-27 (no parameters when elementwise_affine=False)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+
+    def forward(self, x):
+        _standalone_forward_error("LayerNorm2d")
+
+
+class GlobalResponseNorm(nn.Module):
+    """ref/src/modules.py:30-40."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.zeros(1, 1, 1, dim))
+        self.beta = nn.Parameter(torch.zeros(1, 1, 1, dim))
+
+    def forward(self, x):
+        _standalone_forward_error("GlobalResponseNorm")
+
+
+def _mlp_holder(c, dropout):
+    return nn.Sequential(nn.Linear(c, c * 4), nn.GELU(), GlobalResponseNorm(c * 4), nn.Dropout(dropout), nn.Linear(c * 4, c))
+
+
+class ResBlock(nn.Module):
+    """ref/src/modules.py:43-62."""
+
+    def __init__(self, c, c_skip=None, kernel_size=3, dropout=0.0):
+        super().__init__()
+        c_skip = c_skip or 0
+        self.depthwise = nn.Conv2d(c + c_skip, c, kernel_size=kernel_size, padding=kernel_size // 2, groups=c)
+        self.norm = LayerNorm2d(c, elementwise_affine=False, eps=1e-6)
+        self.channelwise = _mlp_holder(c, dropout)
+
+    def forward(self, x, x_skip=None):
+        _standalone_forward_error("ResBlock")
+
+
+class AttnBlock(nn.Module):
+    """ref/src/modules.py:65-79."""
+
+    def __init__(self, c, c_cond, nhead, self_attn=True, dropout=0.0):
+        super().__init__()
+        self.self_attn = self_attn
+        self.norm = LayerNorm2d(c, elementwise_affine=False, eps=1e-6)
+        self.attention = Attention2D(c, nhead, dropout)
+        self.kv_mapper = nn.Sequential(nn.SiLU(), nn.Linear(c_cond, c))
+
+    def forward(self, x, kv, **kwargs):
+        _standalone_forward_error("AttnBlock")
+
+
+class FeedForwardBlock(nn.Module):
+    """ref/src/modules.py:82-96."""
+
+    def __init__(self, c, dropout=0.0):
+        super().__init__()
+        self.norm = LayerNorm2d(c, elementwise_affine=False, eps=1e-6)
+        self.channelwise = _mlp_holder(c, dropout)
+
+    def forward(self, x):
+        _standalone_forward_error("FeedForwardBlock")
+
+
+class TimestepBlock(nn.Module):
+    """ref/src/modules.py:99-106."""
+
+    def __init__(self, c, c_timestep):
+        super().__init__()
+        self.mapper = nn.Linear(c_timestep, c * 2)
+
+    def forward(self, x, t):
+        _standalone_forward_error("TimestepBlock")
+
+
+# ------------------------------------------------------------------------------------------------
+class ConditioningCache:
+    """x- and t-independent conditioning work of one sample() call: c_embed and every AttnBlock's
+    cond K/V for ``batch_total`` samples (conditional rows first, then unconditional rows)."""
+
+    def __init__(self, cache: torch.Tensor, batch_total: int, s_max: int):
+        self.cache, self.batch_total, self.s_max = cache, batch_total, s_max
+
+
+class Paella(nn.Module):
+    """Drop-in for ``Paella`` (ref/src/modules.py:109-283, notebook variant ref/utils/modules.py)."""
+
+    def __init__(self, c_in=256, c_out=256, num_labels=8192, c_r=64, patch_size=2, c_cond=1024,
+                 c_hidden=[640, 1280, 1280], nhead=[-1, 16, 16], blocks=[6, 16, 6], level_config=['CT', 'CTA', 'CTA'],
+                 clip_embd=1024, byt5_embd=1536, clip_seq_len=4, kernel_size=3, dropout=0.1, self_attn=True):
+        super().__init__()
+        self.c_r, self.c_cond, self.num_labels = c_r, c_cond, num_labels
+        self._cfg = dict(c_in=c_in, c_out=c_out, num_labels=num_labels, c_r=c_r, patch_size=patch_size, c_cond=c_cond,
+                         c_hidden=list(c_hidden), nhead=list(nhead), blocks=list(blocks), level_config=list(level_config),
+                         clip_embd=clip_embd, byt5_embd=byt5_embd, clip_seq_len=clip_seq_len, kernel_size=kernel_size,
+                         self_attn=bool(self_attn))
+        if not isinstance(dropout, list):
+            dropout = [dropout] * len(c_hidden)
+
+        self.byt5_mapper = nn.Linear(byt5_embd, c_cond)
+        self.clip_mapper = nn.Linear(clip_embd, c_cond * clip_seq_len)
+        self.clip_image_mapper = nn.Linear(clip_embd, c_cond * clip_seq_len)
+        self.seq_norm = nn.LayerNorm(c_cond, elementwise_affine=False, eps=1e-6)
+        self.in_mapper = nn.Sequential(nn.Embedding(num_labels, c_in), nn.LayerNorm(c_in, elementwise_affine=False, eps=1e-6))
+        self.embedding = nn.Sequential(nn.PixelUnshuffle(patch_size),
+                                       nn.Conv2d(c_in * (patch_size ** 2), c_hidden[0], kernel_size=1),
+                                       LayerNorm2d(c_hidden[0], elementwise_affine=False, eps=1e-6))
+
+        def make(kind, lvl, c_skip=0):
+            c = c_hidden[lvl]
+            if kind == 'C':
+                return ResBlock(c, c_skip, kernel_size=kernel_size, dropout=dropout[lvl])
+            if kind == 'A':
+                return AttnBlock(c, c_cond, nhead[lvl], self_attn=self_attn, dropout=dropout[lvl])
+            if kind == 'F':
+                return FeedForwardBlock(c, dropout=dropout[lvl])
+            if kind == 'T':
+                return TimestepBlock(c, c_r)
+            raise Exception(f'Block type {kind} not supported')
+
+        n = len(c_hidden)
+        self.down_blocks = nn.ModuleList()
+        for i in range(n):
+            level = nn.ModuleList()
+            if i > 0:
+                level.append(nn.Sequential(LayerNorm2d(c_hidden[i - 1], elementwise_affine=False, eps=1e-6),
+                                           nn.Conv2d(c_hidden[i - 1], c_hidden[i], kernel_size=2, stride=2)))
+            for _ in range(blocks[i]):
+                for kind in level_config[i]:
+                    level.append(make(kind, i))
+            self.down_blocks.append(level)
+        self.up_blocks = nn.ModuleList()
+        for i in reversed(range(n)):
+            level = nn.ModuleList()
+            for j in range(blocks[i]):
+                for k, kind in enumerate(level_config[i]):
+                    level.append(make(kind, i, c_skip=c_hidden[i] if i < n - 1 and j == k == 0 else 0))
+            if i > 0:
+                level.append(nn.Sequential(LayerNorm2d(c_hidden[i], elementwise_affine=False, eps=1e-6),
+                                           nn.ConvTranspose2d(c_hidden[i], c_hidden[i - 1], kernel_size=2, stride=2)))
+            self.up_blocks.append(level)
+        self.clf = nn.Sequential(LayerNorm2d(c_hidden[0], elementwise_affine=False, eps=1e-6),
+                                 nn.Conv2d(c_hidden[0], c_out * (patch_size ** 2), kernel_size=1),
+                                 nn.PixelShuffle(patch_size))
+        self.out_mapper = nn.Sequential(LayerNorm2d(c_out, elementwise_affine=False, eps=1e-6),
+                                        nn.Conv2d(c_out, num_labels, kernel_size=1, bias=False))
+        self._reference_init(blocks, num_labels)
+
+        self._handle = None
+        self._blob = None
+        self._packed_key = None
+        self._workspace = None
+        self._cond_single = None
+
+    # -------------------------------------------------------------- initialisation (ref/src/modules.py:189-210)
+    def _reference_init(self, blocks, num_labels):
+        for mod in self.modules():
+            if isinstance(mod, (nn.Conv2d, nn.Linear)):
+                nn.init.xavier_uniform_(mod.weight)
+                if mod.bias is not None:
+                    nn.init.constant_(mod.bias, 0)
+        for lin in (self.byt5_mapper, self.clip_mapper, self.clip_image_mapper):
+            nn.init.normal_(lin.weight, std=0.02)
+        nn.init.xavier_uniform_(self.embedding[1].weight, 0.02)
+        nn.init.constant_(self.clf[1].weight, 0)
+        nn.init.normal_(self.in_mapper[0].weight, std=np.sqrt(1 / num_labels))
+        self.out_mapper[-1].weight.data = self.in_mapper[0].weight.data[:, :, None, None].clone()
+        scale = np.sqrt(1 / sum(blocks))
+        for level in list(self.down_blocks) + list(self.up_blocks):
+            for blk in level:
+                if isinstance(blk, (ResBlock, FeedForwardBlock)):
+                    blk.channelwise[-1].weight.data *= scale
+                elif isinstance(blk, TimestepBlock):
+                    nn.init.constant_(blk.mapper.weight, 0)
+
+    # -------------------------------------------------------------- native handle + packed weights
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                lib().pb200_paella_destroy(self._handle)
+        except Exception:
+            pass
+
+    def _device(self):
+        return self.in_mapper[0].weight.device
+
+    def _weights_key(self):
+        return (str(self._device()),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def pack_weights(self, broadcast_src: Optional[int] = None):
+        """Convert the reference-layout fp32 parameters into the library's packed blob (fp16 GEMM weights,
+        repacked conv kernels, concatenated FiLM mappers).  With ``broadcast_src`` set and
+        ``torch.distributed`` initialised, only that rank converts; the blob is then NCCL-broadcast —
+        the single collective of a multi-GPU run (no collective inside the step loop)."""
+        dev = self._device()
+        if dev.type != "cuda":
+            raise PaellaB200Error("Paella runs on CUDA only: move the model with .to('cuda') (no CPU fallback)")
+        L = lib()
+        if self._handle is None:
+            c = self._cfg
+            cfg = _lib.PaellaConfig()
+            for k in ("c_in", "c_out", "num_labels", "c_r", "patch_size", "c_cond", "clip_embd", "byt5_embd",
+                      "clip_seq_len", "kernel_size"):
+                setattr(cfg, k, int(c[k]))
+            cfg.self_attn = int(c["self_attn"])
+            cfg.n_levels = len(c["c_hidden"])
+            if cfg.n_levels > _lib.PB200_MAX_LEVELS:
+                raise PaellaB200Error("too many levels")
+            for i in range(cfg.n_levels):
+                cfg.c_hidden[i], cfg.nhead[i], cfg.blocks[i] = c["c_hidden"][i], c["nhead"][i], c["blocks"][i]
+                cfg.level_config[i].value = c["level_config"][i].encode()
+            h = ctypes.c_void_p()
+            check(L.pb200_paella_create(ctypes.byref(cfg), ctypes.byref(h)), "pb200_paella_create")
+            self._handle = h
+        with torch.cuda.device(dev):
+            nbytes = L.pb200_paella_weight_bytes(self._handle)
+            if self._blob is None or self._blob.numel() != nbytes or self._blob.device != dev:
+                self._blob = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+                self._workspace = None
+            check(L.pb200_paella_bind_weights(self._handle, ptr(self._blob)), "pb200_paella_bind_weights")
+            import torch.distributed as dist
+            distributed = broadcast_src is not None and dist.is_available() and dist.is_initialized()
+            if not distributed or dist.get_rank() == broadcast_src:
+                sd = self.state_dict()
+                for i in range(L.pb200_paella_num_params(self._handle)):
+                    name = L.pb200_paella_param_name(self._handle, i)
+                    t = sd[name.decode()].detach().to(dtype=torch.float32).contiguous()
+                    check(L.pb200_paella_load_param(self._handle, name, ptr(t), t.numel(), current_stream()),
+                          f"pb200_paella_load_param({name.decode()})")
+                torch.cuda.current_stream().synchronize()     # temporaries from .float() must outlive the copies
+            if distributed:
+                dist.broadcast(self._blob, src=broadcast_src)
+        self._packed_key = self._weights_key()
+        self._cond_single = None
+        return self
+
+    def _ensure_packed(self):
+        if self._handle is None or self._packed_key != self._weights_key():
+            self.pack_weights()
+
+    def _apply(self, fn, *a, **k):      # .to()/.cuda()/.half(): repack lazily
+        self._packed_key = None
+        return super()._apply(fn, *a, **k)
+
+    def _ws(self, nbytes: int) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != self._device():
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self._device())
+        return self._workspace
+
+    # -------------------------------------------------------------- conditioning
+    def prepare_conditioning(self, groups: Sequence[Dict[str, torch.Tensor]], latent_hw=(32, 32)) -> ConditioningCache:
+        """gen_c_embeddings (ref/src/modules.py:223-232) + every AttnBlock's kv_mapper and K/V projection of the
+        conditioning rows, for the concatenation of ``groups`` (e.g. [conditional, unconditional])."""
+        self._ensure_packed()
+        L = lib()
+        dev = self._device()
+        seq = self._cfg["clip_seq_len"]
+
+        def seqlen(g):
+            n = (1 if g.get("clip") is not None else 0)
+            ci = g.get("clip_image")
+            if ci is not None:
+                n += len(ci) if isinstance(ci, (list, tuple)) else 1
+            return g["byt5"].shape[1] + seq * n
+        s_max = max(seqlen(g) for g in groups)
+        bt = sum(g["byt5"].shape[0] for g in groups)
+        with torch.cuda.device(dev):
+            cache = torch.empty(L.pb200_paella_cond_cache_bytes(self._handle, bt, s_max), dtype=torch.uint8, device=dev)
+            ws = self._ws(L.pb200_paella_workspace_bytes(self._handle, bt, latent_hw[0], latent_hw[1], s_max))
+            off = 0
+            keep = []
+            for g in groups:
+                byt5 = g["byt5"].to(device=dev, dtype=torch.float32).contiguous()
+                B = byt5.shape[0]
+                cond = _lib.Cond()
+                cond.byt5, cond.byt5_len = ptr(byt5).value, byt5.shape[1]
+                clip = g.get("clip")
+                if clip is not None:
+                    clip = clip.to(device=dev, dtype=torch.float32).contiguous()
+                    cond.clip = ptr(clip).value
+                ci = g.get("clip_image")
+                if ci is not None:
+                    ci = torch.stack([t.to(device=dev, dtype=torch.float32) for t in ci]) if isinstance(ci, (list, tuple)) \
+                        else ci.to(device=dev, dtype=torch.float32)[None]
+                    ci = ci.contiguous()
+                    cond.clip_image, cond.n_clip_image = ptr(ci).value, ci.shape[0]
+                keep += [byt5, clip, ci]
+                check(L.pb200_paella_prepare_cond(self._handle, ctypes.byref(cond), B, off, bt, s_max, ptr(cache), ptr(ws),
+                                                  ws.numel(), current_stream()), "pb200_paella_prepare_cond")
+                off += B
+        return ConditioningCache(cache, bt, s_max)
+
+    # -------------------------------------------------------------- forward pieces
+    def features(self, x: torch.Tensor, r: torch.Tensor, cond: ConditioningCache, attn_weights=None,
+                 attn_weights_batch: int = 0) -> torch.Tensor:
+        """Everything up to out_mapper's LayerNorm: tokens [Bt,H,W] -> fp32 [Bt*H*W, c_out]."""
+        self._ensure_packed()
+        L = lib()
+        dev = self._device()
+        Bt, H, W = x.shape
+        if Bt != cond.batch_total:
+            raise PaellaB200Error(f"batch {Bt} does not match the conditioning cache ({cond.batch_total})")
+        with torch.cuda.device(dev):
+            x = x.to(device=dev, dtype=torch.int64).contiguous()
+            r = r.to(device=dev, dtype=torch.float32).contiguous()
+            ws = self._ws(L.pb200_paella_workspace_bytes(self._handle, Bt, H, W, cond.s_max))
+            feats = torch.empty(Bt * H * W, self._cfg["c_out"], dtype=torch.float32, device=dev)
+            aw = attn_weights.to(device=dev, dtype=torch.float32).contiguous() if attn_weights is not None else None
+            check(L.pb200_paella_features(self._handle, ptr(x), ptr(r), Bt, H, W, ptr(cond.cache), cond.s_max, ptr(aw),
+                                          aw.numel() if aw is not None else 0, attn_weights_batch, ptr(feats), ptr(ws),
+                                          ws.numel(), current_stream()), "pb200_paella_features")
+        return feats
+
+    def logits_from_features(self, feats: torch.Tensor, batch: int, h: int, w: int) -> torch.Tensor:
+        L = lib()
+        dev = self._device()
+        with torch.cuda.device(dev):
+            out = torch.empty(batch, self.num_labels, h, w, dtype=torch.float32, device=dev)
+            ws = self._ws(feats.numel() * 2 + 256)
+            check(L.pb200_paella_logits(self._handle, ptr(feats), batch, h * w, ptr(out), ptr(ws), ws.numel(),
+                                        current_stream()), "pb200_paella_logits")
+        return out
+
+    def sample_tokens(self, feats: torch.Tensor, batch: int, h: int, w: int, cfg: Optional[float], temperature: float,
+                      generator=None) -> torch.Tensor:
+        """Fused out_mapper + CFG + temperature + multinomial on torch's random stream (ref/src/utils.py:44-50)."""
+        L = lib()
+        dev = self._device()
+        with torch.cuda.device(dev):
+            out = torch.empty(batch, h, w, dtype=torch.int64, device=dev)
+            ws = self._ws(batch * h * w * self._cfg["c_out"] * 2 + 256)
+            seed, off = ops.take_philox(batch * h * w * self.num_labels, dev, generator)
+            check(L.pb200_paella_sample_tokens(self._handle, ptr(feats), batch, h * w, 1 if cfg is not None else 0,
+                                               float(cfg) if cfg is not None else 0.0, float(temperature), seed, off,
+                                               ptr(out), ptr(ws), ws.numel(), current_stream()), "pb200_paella_sample_tokens")
+        return out
+
+    def forward(self, x, r, byt5, clip=None, clip_image=None, x_cat=None, **kwargs):
+        """ref/src/modules.py:263-275 / ref/utils/modules.py:268-282: logits [B, num_labels, H, W] fp32."""
+        if x_cat is not None:
+            x = torch.cat([x, x_cat], dim=1)
+        attn_weights = kwargs.pop("attn_weights", None)
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
+        B, H, W = x.shape
+        cond = self.prepare_conditioning([{"byt5": byt5, "clip": clip, "clip_image": clip_image}], (H, W))
+        feats = self.features(x, r, cond, attn_weights, B if attn_weights is not None else 0)
+        return self.logits_from_features(feats, B, H, W)
+
+    def add_noise(self, x, t, mask=None, random_x=None):
+        """ref/src/modules.py:277-283 on torch's random stream."""
+        if mask is None:
+            return ops.add_noise(x, t, random_x, self.num_labels)
+        if random_x is None:
+            random_x = ops.randint(self.num_labels, x.shape, x.device)
+        return torch.where(mask.bool(), random_x, x), mask
+
+    def get_loss_weight(self, t, mask, min_val=0.3):    # ref/utils/modules.py:290-291 (training helper)
+        return 1 - (1 - mask) * ((1 - t) * (1 - min_val))[:, None, None]

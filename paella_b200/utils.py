@@ -1,0 +1,116 @@
+"""The sampling loop — ``sample()`` in the reference's three signatures over one fused core.
+
+  sample()               ref/src/utils.py:35-55
+  sample_distributed()   ref/src_distributed/utils.py:97-126   (init_x, per-step cfg, sampling_conditional_steps)
+  sample_notebook()      paella_inference.ipynb cell 3          (mode, attn_weights, returns intermediates)
+
+Per step the reference runs two forwards, materialises 2 x [B,8192,H,W] fp32 logits and makes ~20 passes
+over them.  Here: conditional and unconditional rows run as ONE batch of 2B through the denoiser (their
+conditioning K/V are computed once per call, not per step), and the out_mapper GEMM, CFG mix, temperature,
+softmax and multinomial draw are a single kernel.  All random draws (randint, multinomial's exponential_,
+add_noise's rand_like) come from the torch CUDA generator's own Philox stream, consumed op by op like the
+reference does, so ``torch.manual_seed`` means the same thing.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .modules import Paella
+
+
+def _zeros_like_inputs(inputs: Dict[str, torch.Tensor]):
+    return {k: (torch.zeros_like(v) if torch.is_tensor(v) else v) for k, v in inputs.items() if v is not None}
+
+
+def _sample_core(model: Paella, model_inputs, latent_shape, unconditional_inputs, init_x, steps, renoise_steps, temperature,
+                 cfgs, t_start, t_end, sampling_conditional_steps, mode, attn_weights, exact, collect):
+    B, H, W = latent_shape
+    dev = model._device()
+    use_cfg_any = cfgs is not None
+    with torch.inference_mode():
+        init_noise = ops.randint(model.num_labels, (B, H, W), dev)
+        sampled = init_x.to(dev) if init_x is not None else init_noise.clone()
+        t_list = torch.linspace(t_start, t_end, steps + 1)
+        temperatures = torch.linspace(temperature[0], temperature[1], steps)
+        groups = [model_inputs] + ([unconditional_inputs] if use_cfg_any else [])
+        cond_full = model.prepare_conditioning(groups, (H, W))
+        cond_only = None
+        intermediates = []
+        for i in range(steps):
+            guided = use_cfg_any and i < sampling_conditional_steps
+            t = float(t_list[i])
+            if guided:
+                cond = cond_full
+                tokens = torch.cat([sampled, sampled], dim=0)
+            elif use_cfg_any:
+                if cond_only is None:
+                    cond_only = model.prepare_conditioning([model_inputs], (H, W))
+                cond, tokens = cond_only, sampled
+            else:
+                cond, tokens = cond_full, sampled
+            r = torch.full((tokens.shape[0],), t, dtype=torch.float32, device=dev)
+            feats = model.features(tokens, r, cond, attn_weights, B if attn_weights is not None else 0)
+            cfg_i = float(cfgs[i]) if guided else None
+            if mode == "multinomial" and not exact:
+                sampled = model.sample_tokens(feats, B, H, W, cfg_i, float(temperatures[i]))
+            else:
+                n = B * H * W
+                lc = model.logits_from_features(feats[:n], B, H, W)
+                lu = model.logits_from_features(feats[n:], B, H, W) if guided else None
+                if mode == "quant":
+                    raise NotImplementedError("mode='quant' (softmax @ codebook -> re-quantise) is not built yet")
+                sampled = ops.resample_logits(lc, lu, cfg_i if guided else 0.0, float(temperatures[i]), mode)
+            if collect:
+                intermediates.append(sampled)
+            if i < renoise_steps:
+                t_next = torch.full((B,), float(t_list[i + 1]), dtype=torch.float32, device=dev)
+                sampled = model.add_noise(sampled, t_next, random_x=init_noise)[0]
+                if collect:
+                    intermediates.append(sampled)
+    return sampled, intermediates
+
+
+def sample(model, model_inputs, latent_shape, unconditional_inputs=None, steps=12, renoise_steps=11, temperature=(1.0, 0.2),
+           cfg=8.0, t_start=1.0, t_end=0.0, device="cuda", exact=False):
+    """ref/src/utils.py:35-55 (same positional/keyword arguments; ``device`` is accepted and must be the model's).
+    ``exact=True`` materialises the logits and uses the op-for-op torch arithmetic (parity path)."""
+    cfgs = [cfg] * steps if cfg else None
+    if cfgs is not None and unconditional_inputs is None:
+        raise TypeError("sample(): cfg is set but unconditional_inputs is None")
+    out, _ = _sample_core(model, model_inputs, tuple(latent_shape), unconditional_inputs, None, steps, renoise_steps,
+                          temperature, cfgs, t_start, t_end, steps, "multinomial", None, exact, False)
+    return out
+
+
+def sample_distributed(model, model_inputs, unconditional_inputs, latent_shape, init_x=None, steps=12, renoise_steps=None,
+                       temperature=(0.7, 0.3), cfg=(8.0, 8.0), t_start=1.0, t_end=0.0, sampling_conditional_steps=None,
+                       exact=False):
+    """ref/src_distributed/utils.py:97-126."""
+    if sampling_conditional_steps is None:
+        sampling_conditional_steps = steps
+    if renoise_steps is None:
+        renoise_steps = steps - 1
+    cfgs = torch.linspace(cfg[0], cfg[1], steps).tolist() if cfg is not None else None
+    out, _ = _sample_core(model, model_inputs, tuple(latent_shape), unconditional_inputs, init_x, steps, renoise_steps,
+                          temperature, cfgs, t_start, t_end, sampling_conditional_steps, "multinomial", None, exact, False)
+    return out
+
+
+def sample_notebook(model, model_inputs, latent_shape, unconditional_inputs=None, init_x=None, steps=12, renoise_steps=None,
+                    temperature=(0.7, 0.3), cfg=(8.0, 8.0), mode='multinomial', t_start=1.0, t_end=0.0,
+                    sampling_conditional_steps=None, sampling_quant_steps=None, attn_weights=None, exact=False):
+    """paella_inference.ipynb cell 3: returns (sampled, intermediate_images)."""
+    if sampling_conditional_steps is None:
+        sampling_conditional_steps = steps
+    if sampling_quant_steps is not None and sampling_quant_steps < steps:
+        raise NotImplementedError("sampling_quant_steps (switch to mode='quant') is not built yet")
+    if renoise_steps is None:
+        renoise_steps = steps - 1
+    if unconditional_inputs is None:
+        unconditional_inputs = _zeros_like_inputs(model_inputs)
+    cfgs = torch.linspace(cfg[0], cfg[1], steps).tolist() if cfg is not None else None
+    return _sample_core(model, model_inputs, tuple(latent_shape), unconditional_inputs, init_x, steps, renoise_steps,
+                        temperature, cfgs, t_start, t_end, sampling_conditional_steps, mode, attn_weights, exact, True)

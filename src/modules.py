@@ -1,0 +1,3 @@
+"""Import-path shim for the reference's ``src/modules.py`` -> paella_b200.modules (same class surface)."""
+from paella_b200.modules import (Attention2D, AttnBlock, FeedForwardBlock, GlobalResponseNorm, LayerNorm2d, Paella,  # noqa: F401
+                                 ResBlock, TimestepBlock)

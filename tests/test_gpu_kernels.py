@@ -260,8 +260,8 @@ def test_gemm_unpatchify_and_nchw_and_remap():
     B, h, w_, cin, cout = 3, 8, 8, 128, 64
     a = torch.randn(B * h * w_, cin, device=DEV, generator=g).half()
     wt = (torch.randn(4 * cout, cin, device=DEV, generator=g) / math.sqrt(cin)).half()
-    bias = torch.randn(cout, device=DEV, generator=g)
-    y = (_ref_mm(a, wt)).view(B, h, w_, 2, 2, cout) + bias
+    bias = torch.randn(4 * cout, device=DEV, generator=g)
+    y = (_ref_mm(a, wt) + bias).view(B, h, w_, 2, 2, cout)
     want = y.permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * h, 2 * w_, cout)
     out = torch.zeros(B, 2 * h, 2 * w_, cout, device=DEV)
     ops.gemm_f16(a, wt, _lib.EPI_UNPATCH_F32, out, bias=bias, up=(h, w_, cout))
