@@ -27,6 +27,13 @@ int pb200_abi_version(void);
 /* multiprocessor count / max threads per SM of the current device (they fix PyTorch's Philox launch policy). */
 int pb200_device_info(int* sm_count, int* max_threads_per_sm);
 
+/* Measurement hooks used by bench.py: number of kernel launches the library has made so far, and optional
+ * CUDA-event bracketing of every launch by kernel family (report: JSON {family: {launches, ms, work}},
+ * work = algorithmic FLOPs for GEMM-shaped kernels, bytes otherwise). */
+long long pb200_launch_count(void);
+int pb200_profile_enable(int on);
+int pb200_profile_report(char* buf, long long cap);
+
 /* ------------------------------------------------------------------------------------------
  * Random streams and the resample step.  `seed`/`offset` are the (seed, philox offset) of the
  * torch CUDA generator BEFORE the op; each op consumes pb200_philox_offset_increment(numel)

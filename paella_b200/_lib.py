@@ -50,6 +50,9 @@ SIGNATURES = {
     "pb200_last_error": (c_char_p, []),
     "pb200_abi_version": (c_int, []),
     "pb200_device_info": (c_int, [POINTER(c_int), POINTER(c_int)]),
+    "pb200_launch_count": (ctypes.c_longlong, []),
+    "pb200_profile_enable": (c_int, [c_int]),
+    "pb200_profile_report": (c_int, [c_char_p, ctypes.c_longlong]),
     "pb200_philox_offset_increment": (c_int64, [c_int64]),
     "pb200_randint": (c_int, [c_void_p, c_int64, c_int64, c_uint64, c_uint64, c_void_p]),
     "pb200_rand": (c_int, [c_void_p, c_int64, c_uint64, c_uint64, c_void_p]),

@@ -33,7 +33,11 @@ const char* last_error();
         }                                                                               \
     } while (0)
 
-#define PB_LAUNCH_CHECK() PB_CUDA(cudaGetLastError())
+#define PB_LAUNCH_CHECK()            \
+    do {                             \
+        pb::prof_count_launch();     \
+        PB_CUDA(cudaGetLastError()); \
+    } while (0)
 
 #define PB_TRY(expr)                 \
     do {                             \
@@ -45,6 +49,18 @@ inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 int sm_count();        // multiprocessor count of the current device (cached)
 int max_threads_per_sm();
+
+// ---------------------------------------------------------------- measurement hooks (bench.py)
+void prof_count_launch();            // every kernel launch of the library bumps one counter
+bool prof_enabled();
+// When profiling is on, brackets the launches made in its scope with CUDA events on `st`, tagged with a kernel
+// family and its algorithmic work (FLOPs for GEMM-shaped kernels, bytes otherwise).
+struct ProfScope {
+    int slot;
+    cudaStream_t st;
+    ProfScope(const char* tag, double work, cudaStream_t s);
+    ~ProfScope();
+};
 
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ float warp_sum(float v) {

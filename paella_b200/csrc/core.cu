@@ -1,8 +1,13 @@
-// Error plumbing and device queries shared by the whole library.
+// Error plumbing, device queries and the measurement hooks shared by the whole library.
 #include "common.cuh"
 #include "paella_b200.h"
 
+#include <atomic>
+#include <cstring>
+#include <map>
 #include <mutex>
+#include <sstream>
+#include <vector>
 
 namespace pb {
 
@@ -28,6 +33,37 @@ static void query_device() {
 int sm_count() { query_device(); return g_sm; }
 int max_threads_per_sm() { query_device(); return g_tpsm; }
 
+// ------------------------------------------------------------------ measurement hooks
+static std::atomic<long long> g_launches{0};
+static bool g_prof = false;
+struct ProfRec {
+    std::string tag;
+    double work;
+    cudaEvent_t e0, e1;
+};
+static std::vector<ProfRec> g_recs;
+static std::mutex g_prof_mu;
+
+void prof_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool prof_enabled() { return g_prof; }
+
+ProfScope::ProfScope(const char* tag, double work, cudaStream_t s) : slot(-1), st(s) {
+    if (!g_prof) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    r.tag = tag;
+    r.work = work;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, st);
+    slot = (int)g_recs.size();
+    g_recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_recs[slot].e1, st);
+}
+
 }  // namespace pb
 
 extern "C" {
@@ -37,6 +73,48 @@ int pb200_device_info(int* sms, int* tpsm) {
     PB_CHECK(pb::sm_count() > 0, "no CUDA device");
     if (sms) *sms = pb::sm_count();
     if (tpsm) *tpsm = pb::max_threads_per_sm();
+    return 0;
+}
+
+long long pb200_launch_count(void) { return pb::g_launches.load(); }
+
+int pb200_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(pb::g_prof_mu);
+    for (auto& r : pb::g_recs) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    pb::g_recs.clear();
+    pb::g_prof = on != 0;
+    return 0;
+}
+
+// Synchronises the device and writes a JSON object {tag: {"launches": n, "ms": total, "work": total}} into buf.
+int pb200_profile_report(char* buf, long long cap) {
+    PB_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(pb::g_prof_mu);
+    struct Agg { long long n = 0; double ms = 0, work = 0; };
+    std::map<std::string, Agg> agg;
+    for (auto& r : pb::g_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+        Agg& a = agg[r.tag];
+        a.n += 1; a.ms += ms; a.work += r.work;
+    }
+    std::ostringstream os;
+    os.precision(9);
+    os << "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        if (!first) os << ", ";
+        first = false;
+        os << "\"" << kv.first << "\": {\"launches\": " << kv.second.n << ", \"ms\": " << kv.second.ms << ", \"work\": "
+           << kv.second.work << "}";
+    }
+    os << "}";
+    const std::string s = os.str();
+    PB_CHECK((long long)s.size() + 1 <= cap, "profile_report: buffer too small");
+    memcpy(buf, s.c_str(), s.size() + 1);
     return 0;
 }
 }

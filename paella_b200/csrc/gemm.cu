@@ -377,6 +377,8 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const
     if ((ep.mode == PB200_EPI_GELU_F16 && ep.sqsum) || (ep.mode == PB200_EPI_RESID_F32 && ep.film) ||
         ep.mode == PB200_EPI_NCHW_F32)
         PB_CHECK(ep.rows_per_sample > 0, "gemm: rows_per_sample required");
+    static const char* kTags[6] = {"gemm_f16", "gemm_f32", "gemm_gelu_sqsum", "gemm_resid", "gemm_unpatch", "gemm_nchw"};
+    ProfScope prof(ep.mode >= 0 && ep.mode < 6 ? kTags[ep.mode] : "gemm", 2.0 * (double)M * (double)N * (double)K, st);
     switch (block_n) {
         case 64: return launch_mode<64>(ta, tb, ep, (int)M, (int)N, (int)K, st);
         case 128: return launch_mode<128>(ta, tb, ep, (int)M, (int)N, (int)K, st);

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(const int64_t* __rest
 
 int launch_embed_tokens(const int64_t* tokens, const float* emb, int num_labels, int c_in, int B, int H, int W, int ps,
                         __half* out, cudaStream_t st) {
+    ProfScope prof("embed_tokens", (double)B * H * W * c_in * 6.0, st);
     PB_CHECK(H % ps == 0 && W % ps == 0, "embed: latent %dx%d not divisible by patch_size %d", H, W, ps);
     const int64_t rows = (int64_t)B * (H / ps) * (W / ps);
     const size_t smem = (size_t)8 * c_in * ps * ps * sizeof(__half);
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
 
 int launch_ln_rows(const float* x, int64_t rows, int C, float scale, float shift, __half* out16, float* out32,
                    cudaStream_t st) {
+    ProfScope prof("layernorm", (double)rows * C * (out16 ? 6.0 : 8.0), st);
     PB_CHECK(C % 4 == 0, "layernorm: C=%d must be a multiple of 4", C);
     PB_CHECK((out16 != nullptr) != (out32 != nullptr), "layernorm: exactly one output");
     if (rows == 0) return 0;
@@ -119,6 +121,7 @@ int launch_ln_rows(const float* x, int64_t rows, int C, float scale, float shift
 }
 
 int launch_ln_patchify2(const float* x, int B, int h, int w, int c, __half* out, cudaStream_t st) {
+    ProfScope prof("layernorm", (double)B * h * w * c * 6.0, st);
     PB_CHECK(c % 4 == 0 && h % 2 == 0 && w % 2 == 0, "ln_patchify: bad geometry %dx%dx%d", h, w, c);
     const int64_t rows = (int64_t)B * h * w;
     ln_rows_kernel<true><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, c, 1.0f, 0.0f, out, nullptr, h, w);
@@ -228,6 +231,7 @@ static int dwconv_dispatch(const float* x, const float* skip, const float* wp, c
 
 int launch_dwconv_ln(const float* x, const float* skip, const float* w_packed, const float* bias, int B, int h, int w,
                      int c, int k, __half* out, cudaStream_t st) {
+    ProfScope prof("dwconv_ln", (double)B * h * w * c * (skip ? 10.0 : 6.0), st);
     PB_CHECK(c % 8 == 0, "dwconv: c=%d must be a multiple of 8", c);
     PB_CHECK(k % 2 == 1, "dwconv: kernel_size %d must be odd", k);
     if (c <= 128) return dwconv_dispatch<1>(x, skip, w_packed, bias, B, h, w, c, k, out, st);
@@ -280,12 +284,14 @@ __global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ h, 
 }
 
 int launch_grn_scale(float* sqsum, const float* gamma, int B, int N, float* scale, cudaStream_t st) {
+    ProfScope prof("grn", (double)B * N * 12.0, st);
     grn_scale_kernel<<<B, 256, 0, st>>>(sqsum, gamma, N, scale);
     PB_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_grn_apply(__half* h, int64_t M, int N, int P, const float* scale, const float* beta, cudaStream_t st) {
+    ProfScope prof("grn", (double)M * N * 4.0, st);
     PB_CHECK(N % 8 == 0, "grn: N=%d must be a multiple of 8", N);
     grn_apply_kernel<<<ceil_div(M * (N / 8), 256), 256, 0, st>>>(h, M, N, P, scale, beta);
     PB_LAUNCH_CHECK();
@@ -307,6 +313,7 @@ __global__ void r_embed_kernel(const float* __restrict__ r, int B, int c_r, floa
 }
 
 int launch_r_embed(const float* r, int B, int c_r, float* out, cudaStream_t st) {
+    ProfScope prof("film", (double)B * c_r * 4.0, st);
     PB_CHECK(c_r >= 4, "c_r=%d too small", c_r);
     r_embed_kernel<<<ceil_div((long)B * c_r, 128), 128, 0, st>>>(r, B, c_r, out);
     PB_LAUNCH_CHECK();
@@ -356,6 +363,7 @@ __global__ void film_table_generic_kernel(const float* __restrict__ r_embed, int
 
 int launch_film_table(const float* r_embed, int B, int c_r, const float* W, const float* bias, int total, float* out,
                       cudaStream_t st) {
+    ProfScope prof("film", (double)total * (c_r + B) * 4.0, st);
     if (total == 0) return 0;
     if (c_r == 64)
         film_table_kernel<64><<<ceil_div(total, 128), 128, 64 * 64 * sizeof(float), st>>>(r_embed, B, W, bias, total, out);
@@ -382,6 +390,7 @@ __global__ void film_apply_kernel(float* __restrict__ x, int64_t M, int N, int P
 
 int launch_film_apply(float* x, int64_t M, int N, int P, const float* film, int64_t film_ld, int64_t film_off,
                       cudaStream_t st) {
+    ProfScope prof("film", (double)M * N * 8.0, st);
     PB_CHECK(N % 4 == 0 && film_off % 4 == 0 && film_ld % 4 == 0, "film: misaligned table");
     film_apply_kernel<<<ceil_div(M * (N / 4), 256), 256, 0, st>>>(x, M, N, P, film, film_ld, film_off);
     PB_LAUNCH_CHECK();
@@ -413,18 +422,21 @@ __global__ void cast_kernel(const float* __restrict__ a, const float* __restrict
 }
 
 int launch_cast_f16(const float* x, int64_t n, __half* out, cudaStream_t st) {
+    ProfScope prof("cast", (double)n * 6.0, st);
     if (n == 0) return 0;
     cast_kernel<0><<<ceil_div(ceil_div(n, 4), 256), 256, 0, st>>>(x, nullptr, 1.f, 0.f, n, out);
     PB_LAUNCH_CHECK();
     return 0;
 }
 int launch_silu_cast_f16(const float* x, int64_t n, __half* out, cudaStream_t st) {
+    ProfScope prof("cast", (double)n * 6.0, st);
     if (n == 0) return 0;
     cast_kernel<1><<<ceil_div(ceil_div(n, 4), 256), 256, 0, st>>>(x, nullptr, 1.f, 0.f, n, out);
     PB_LAUNCH_CHECK();
     return 0;
 }
 int launch_mix_cast_f16(const float* a, const float* b, float wa, float wb, int64_t n, __half* out, cudaStream_t st) {
+    ProfScope prof("cast", (double)n * (b ? 10.0 : 6.0), st);
     if (n == 0) return 0;
     cast_kernel<2><<<ceil_div(ceil_div(n, 4), 256), 256, 0, st>>>(a, b, wa, wb, n, out);
     PB_LAUNCH_CHECK();

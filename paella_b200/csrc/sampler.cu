@@ -173,6 +173,7 @@ int launch_fused_sampler(const __half* a16, int64_t R, int Kc, const __half* w16
         PB_CUDA(cudaFuncSetAttribute(fused_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMP_SMEM));
         attr_set = true;
     }
+    ProfScope prof("fused_sampler", 2.0 * (double)R * (double)NL * (double)Kc, st);
     CUtensorMap ta, tw;
     PB_TRY(make_tmap_f16_2d(&ta, a16, R, Kc, Kc, 128));
     PB_TRY(make_tmap_f16_2d(&tw, w16, NL, Kc, Kc, SMP_BN));
