@@ -31,6 +31,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec @256x256-class (32x32 latent, 8192 codes), 8-step CFG sample, bs=64 per GPU"
 LATENT, SAMPLE_STEPS, RENOISE, BYT5_LEN, BATCH = 32, 8, 7, 128, 64
+WORKLOAD = ("sample() 8-step CFG, 32x32 latents, 8192 codes, 1.008B denoiser (reference default; readme says 573M), "
+            "L_byt5=128+clip, synthetic embeddings, re-randomised weights")
 
 
 def peaks():
@@ -127,8 +129,7 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "sample() 8-step CFG, 32x32 latents, 8192 codes, 1.008B denoiser (reference default), L_byt5=128+clip",
-                   "batch_per_step": B},
+        "config": {"workload": WORKLOAD, "batch_per_step": B},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
@@ -243,9 +244,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
            "data": "synthetic",
-           "config": {"workload": "sample() 8-step CFG, 32x32 latents, 8192 codes, 1.008B denoiser (reference default; readme says 573M), "
-                                  "L_byt5=128+clip, synthetic embeddings, re-randomised weights",
-                      "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-shard x{world}, 1 weight broadcast",
+           "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-shard x{world}, 1 weight broadcast",
                       "l2": "inputs larger than L2 (2.0 GB fp16 weights + activations per step)"},
            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": ms_e2e / args.steps},

@@ -55,6 +55,32 @@ int make_tmap_f16_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t col
     return 0;
 }
 
+// rank-N fp16 tensor map (dims/strides innermost first, strides in bytes for dims 1..rank-1), 128-byte swizzle
+int make_tmap_f16_nd(CUtensorMap* tm, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes,
+                     const int* box) {
+    EncodeTiledFn fn = encode_fn();
+    PB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    PB_CHECK(rank >= 2 && rank <= 5, "TMA: rank %d unsupported", rank);
+    PB_CHECK(((uintptr_t)ptr & 15) == 0, "TMA: base pointer must be 16-byte aligned");
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], e[5];
+    for (int i = 0; i < rank; ++i) {
+        d[i] = (cuuint64_t)dims[i];
+        b[i] = (cuuint32_t)box[i];
+        e[i] = 1;
+        PB_CHECK(box[i] >= 1 && box[i] <= 256, "TMA: bad box[%d]=%d", i, box[i]);
+        if (i > 0) {
+            PB_CHECK(strides_bytes[i - 1] % 16 == 0, "TMA: stride %lld not a multiple of 16 bytes", (long long)strides_bytes[i - 1]);
+            s[i - 1] = (cuuint64_t)strides_bytes[i - 1];
+        }
+    }
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, s, b, e,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rank %d) failed (%d)", rank, (int)r);
+    return 0;
+}
+
 // ------------------------------------------------------------------ epilogue
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, int M, int N, int row, int col0,
@@ -192,10 +218,13 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
 }
 
 // ------------------------------------------------------------------ kernel
-template <int BLOCK_N, int MODE>
+// AMODE 0: A is a [M,K] matrix.  AMODE 1/2: A rows are gathered by TMA straight from an NHWC fp16 activation
+// (im2col-free convolution): a 128-row tile is a th x tw patch of the output grid and k-block kb selects a filter
+// tap and a 64-channel slice; out-of-image taps are zero-filled by the TMA unit (the conv's zero padding).
+template <int BLOCK_N, int MODE, int AMODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                const pb200_gemm_epilogue ep, int M, int N, int K) {
+                const pb200_gemm_epilogue ep, const ConvGeom geom, int M, int N, int K) {
     using L = GemmSmem<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -210,7 +239,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const int n_tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
-    const int n_tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * n_tiles_n;
+    const int n_tiles_m = AMODE == 0 ? (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M : geom.batch * geom.tiles_y * geom.tiles_x;
+    const int n_tiles = n_tiles_m * n_tiles_n;
     const int n_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
 
     if (warp == 0 && lane == 0) {
@@ -225,7 +255,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             }
             for (int s = 0; s < 2; ++s) {
                 ptx::mbar_init(tfull_bar(s), 1);
-                ptx::mbar_init(tempty_bar(s), 4);       // one arrival per epilogue warp
+                ptx::mbar_init(tempty_bar(s), GEMM_EPI_WARPS);       // one arrival per epilogue warp
             }
             ptx::fence_barrier_init();
         }
@@ -244,13 +274,38 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m_idx = (tile / n_tiles_n) * GEMM_BLOCK_M;
+                const int mt = tile / n_tiles_n;
+                const int m_idx = mt * GEMM_BLOCK_M;
                 const int n_idx = (tile % n_tiles_n) * BLOCK_N;
+                int cb = 0, cy0 = 0, cx0 = 0;
+                if (AMODE != 0) {
+                    cb = mt / (geom.tiles_y * geom.tiles_x);
+                    const int r = mt - cb * geom.tiles_y * geom.tiles_x;
+                    cy0 = (r / geom.tiles_x) * geom.th;
+                    cx0 = (r % geom.tiles_x) * geom.tw;
+                }
                 for (int kb = 0; kb < n_kb; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1);
                     ptx::mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
-                    ptx::tma_load_2d(&tm_a, full_bar(stage), sa, kb * GEMM_BLOCK_K, m_idx);
+                    if (AMODE == 0) {
+                        ptx::tma_load_2d(&tm_a, full_bar(stage), sa, kb * GEMM_BLOCK_K, m_idx);
+                    } else if (AMODE == 1) {
+                        // Conv2d(k=4, s=2, p=1): tap (ky,kx) reads input (2y-1+ky, 2x-1+kx) = parity plane (pa,pb) at
+                        // (y+a, x+b) of the [B, H/2, 2, W/2, 2*C] view
+                        const int tap = kb / geom.n_cchunk, cc = kb - tap * geom.n_cchunk;
+                        const int dy = (tap >> 2) - 1, dx = (tap & 3) - 1;
+                        const int a = dy < 0 ? -1 : (dy >> 1), b = dx < 0 ? -1 : (dx >> 1);
+                        const int pa = dy - 2 * a, pb = dx - 2 * b;
+                        ptx::tma_load_5d(&tm_a, full_bar(stage), sa, pb * geom.cin + cc * 64, cx0 + b, pa, cy0 + a, cb);
+                    } else {
+                        // ConvTranspose2d(k=4, s=2, p=1), output phase (py,px): 2x2 taps at (y+oy, x+ox)
+                        const int tap = kb / geom.n_cchunk, cc = kb - tap * geom.n_cchunk;
+                        const int ty = tap >> 1, tx = tap & 1;
+                        const int oy = geom.py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0);
+                        const int ox = geom.px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0);
+                        ptx::tma_load_4d(&tm_a, full_bar(stage), sa, cc * 64, cx0 + ox, cy0 + oy, cb);
+                    }
                     ptx::tma_load_2d(&tm_b, full_bar(stage), sa + L::A_BYTES, kb * GEMM_BLOCK_K, n_idx);
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -290,17 +345,30 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     } else {
         // ===================== epilogue =====================
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;       // which half of the tile's columns (two warps share a quarter)
+        constexpr int COLS_PER_WARP = BLOCK_N / (GEMM_EPI_WARPS / 4);
         int iter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
-            const int m_idx = (tile / n_tiles_n) * GEMM_BLOCK_M;
+            const int mt = tile / n_tiles_n;
+            const int m_idx = mt * GEMM_BLOCK_M;
             const int n_idx = (tile % n_tiles_n) * BLOCK_N;
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
-            const int row = m_idx + q * 32 + lane;
+            int row = m_idx + q * 32 + lane;
+            if (AMODE != 0) {   // tile row r = (ly, lx) of a th x tw patch -> output pixel row of the NHWC result
+                const int cb = mt / (geom.tiles_y * geom.tiles_x);
+                const int rr = mt - cb * geom.tiles_y * geom.tiles_x;
+                const int r = q * 32 + lane;
+                const int gy = (rr / geom.tiles_x) * geom.th + r / geom.tw;
+                const int gx = (rr % geom.tiles_x) * geom.tw + r % geom.tw;
+                row = (gy < geom.gh && gx < geom.gw)
+                          ? ((cb * geom.oh + gy * geom.sy + geom.py) * geom.ow + gx * geom.sx + geom.px)
+                          : M;      // M = B*oh*ow: out of range -> masked
+            }
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
+            for (int c = half * COLS_PER_WARP; c < (half + 1) * COLS_PER_WARP; c += 32) {
                 if (n_idx + c >= N) break;
                 float v[32];
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c), v);
@@ -317,21 +385,48 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ dispatch
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int AMODE = 0>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_gemm_epilogue& ep, int M, int N, int K,
-                      cudaStream_t st) {
+                      cudaStream_t st, const ConvGeom* geom = nullptr) {
     using L = GemmSmem<BLOCK_N>;
     static bool attr_set = false;
     if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PB_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BLOCK_N, MODE, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      L::SMEM_BYTES));
         attr_set = true;
     }
-    const int n_tiles = ceil_div(M, GEMM_BLOCK_M) * ceil_div(N, BLOCK_N);
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    if (geom) g = *geom;
+    const int tiles_m = AMODE == 0 ? ceil_div(M, GEMM_BLOCK_M) : g.batch * g.tiles_y * g.tiles_x;
+    const int n_tiles = tiles_m * ceil_div(N, BLOCK_N);
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    gemm_f16_kernel<BLOCK_N, MODE><<<grid, GEMM_THREADS, L::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K);
+    gemm_f16_kernel<BLOCK_N, MODE, AMODE><<<grid, GEMM_THREADS, L::SMEM_BYTES, st>>>(ta, tb, ep, g, M, N, K);
     PB_LAUNCH_CHECK();
     return 0;
+}
+
+// im2col-free convolution: A gathered from an NHWC fp16 activation (see ConvGeom); fp32 NHWC output (+bias)
+int gemm_conv_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const pb200_gemm_epilogue& ep,
+                     const ConvGeom& geom, int64_t N, int64_t K, cudaStream_t st) {
+    PB_CHECK(ep.mode == PB200_EPI_F32, "conv gemm: only the fp32 store epilogue is instantiated");
+    PB_CHECK(geom.mode == 1 || geom.mode == 2, "conv gemm: bad mode");
+    PB_CHECK(geom.tw * geom.th == GEMM_BLOCK_M, "conv gemm: tile must cover 128 positions");
+    const int64_t M = (int64_t)geom.batch * geom.oh * geom.ow;     // rows of the output tensor (mask value in-kernel)
+    PB_CHECK(M < (1ll << 31) && N % 8 == 0, "conv gemm: problem too large / N not a multiple of 8");
+    ProfScope prof(geom.mode == 1 ? "conv_k4s2" : "convT_k4s2", 2.0 * (double)geom.batch * geom.gh * geom.gw * (double)N * (double)K, st);
+#define PB_CONV_CASE(BN)                                                                                           \
+    case BN:                                                                                                       \
+        return geom.mode == 1 ? launch_cfg<BN, PB200_EPI_F32, 1>(ta, tb, ep, (int)M, (int)N, (int)K, st, &geom)    \
+                              : launch_cfg<BN, PB200_EPI_F32, 2>(ta, tb, ep, (int)M, (int)N, (int)K, st, &geom);
+    switch (block_n) {
+        PB_CONV_CASE(64)
+        PB_CONV_CASE(128)
+        PB_CONV_CASE(256)
+    }
+#undef PB_CONV_CASE
+    PB_CHECK(false, "conv gemm: unsupported BLOCK_N %d", block_n);
+    return 1;
 }
 
 template <int BLOCK_N>

@@ -8,7 +8,8 @@ namespace pb {
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;     // 64 fp16 = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192;    // TMA warp, MMA warp, 4 epilogue warps
+constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;    // TMA warp, MMA warp, epilogue warps
 
 template <int BLOCK_N>
 struct GemmSmem {
@@ -23,6 +24,25 @@ struct GemmSmem {
 // 2-D fp16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements):
 // box = 64 columns x box_rows rows, 128-byte swizzle, zero fill out of bounds.
 int make_tmap_f16_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
+int make_tmap_f16_nd(CUtensorMap* tm, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes,
+                     const int* box);
+
+// A operand gathered from an NHWC fp16 activation instead of a matrix (im2col-free convolutions of the VQGAN):
+//   mode 1  Conv2d(k=4,s=2,p=1):        5-D map over the [B, H/2, 2, W/2, 2*C] view, 16 taps
+//   mode 2  ConvTranspose2d(k=4,s=2,p=1), one output phase (py,px): 4-D map [B,H,W,C], 4 taps
+struct ConvGeom {
+    int mode;
+    int batch;
+    int tw, th;               // a 128-row tile = th x tw positions of the GEMM-row grid
+    int tiles_x, tiles_y;
+    int gh, gw;               // GEMM-row grid (mode 1: conv output grid; mode 2: convT input grid)
+    int cin, n_cchunk;        // input channels, ceil(cin / 64)
+    int oh, ow, sy, sx, py, px;   // output pixel of grid position (y,x): ((b*oh + y*sy + py)*ow + x*sx + px)
+};
+
+int gemm_conv_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const pb200_gemm_epilogue& ep,
+                     const ConvGeom& geom, int64_t N, int64_t K, cudaStream_t st);
 
 int gemm_pick_block_n(int64_t M, int64_t N);
 
