@@ -121,7 +121,7 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
         }
     } else if (MODE == PB200_EPI_GELU_F16) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
         if (row_ok) {
             __half* o = reinterpret_cast<__half*>(ep.out) + (int64_t)row * ep.ldo + col0;
 #pragma unroll
