@@ -26,6 +26,14 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// 16-byte asynchronous global->shared copy; src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 constexpr int ATT_BM = 64;   // queries per CTA (4 warps x 16)
 constexpr int ATT_BN = 64;   // keys per chunk
 constexpr float NEG_BIG = -1e30f;
@@ -34,9 +42,10 @@ template <int HD>
 __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     constexpr int LDS = HD + 8;           // padded row: (HD+8)*2 bytes is an odd multiple of 16 -> conflict-free ldmatrix
     constexpr int CPR = HD / 8;           // 16-byte chunks per row
-    __shared__ __align__(16) __half sQ[ATT_BM * LDS];
-    __shared__ __align__(16) __half sK[ATT_BN * LDS];
-    __shared__ __align__(16) __half sV[ATT_BN * LDS];
+    extern __shared__ __align__(16) __half smem_att[];
+    __half* sQ = smem_att;                                   // [ATT_BM][LDS]
+    __half* sKb = smem_att + ATT_BM * LDS;                    // [2][ATT_BN][LDS]   double-buffered K
+    __half* sVb = sKb + 2 * ATT_BN * LDS;                     // [2][ATT_BN][LDS]   double-buffered V
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -49,6 +58,31 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     const __half* qkv_b = p.qkv + (int64_t)b * p.P * ldq;
     const __half* ckv_b = p.ckv + (int64_t)b * p.S_max * ldc;
 
+    // K/V chunk j0.. -> buffer `buf` with 16-byte cp.async (zero-fill for keys past the end)
+    auto load_chunk = [&](int j0, int buf) {
+        __half* sK = sKb + buf * ATT_BN * LDS;
+        __half* sV = sVb + buf * ATT_BN * LDS;
+        for (int c = tid; c < ATT_BN * CPR; c += 128) {
+            const int r = c / CPR, cc = c - r * CPR;
+            const int j = j0 + r;
+            const __half *ks = qkv_b, *vs = qkv_b;
+            uint32_t nbytes = 0;
+            if (j < n_self) {
+                ks = qkv_b + (int64_t)j * ldq + h * HD + cc * 8 + E;
+                vs = ks + E;
+                nbytes = 16;
+            } else if (j < Nk) {
+                ks = ckv_b + (int64_t)(j - n_self) * ldc + h * HD + cc * 8;
+                vs = ks + E;
+                nbytes = 16;
+            }
+            cp_async16(smem_u32(sK + r * LDS + cc * 8), ks, nbytes);
+            cp_async16(smem_u32(sV + r * LDS + cc * 8), vs, nbytes);
+        }
+    };
+    load_chunk(0, 0);
+    cp_async_commit();
+
     for (int c = tid; c < ATT_BM * CPR; c += 128) {
         const int r = c / CPR, cc = c - r * CPR;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -56,6 +90,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
         *reinterpret_cast<uint4*>(sQ + r * LDS + cc * 8) = v;
     }
     __syncthreads();
+    const bool warp_active = q0 + warp * 16 < p.P;           // warps past the last query only help with the loads
     uint32_t qf[HD / 16][4];
 #pragma unroll
     for (int ks = 0; ks < HD / 16; ++ks)
@@ -69,25 +104,16 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     const bool weighted = p.attn_w != nullptr && b < p.w_batch && p.n_w > 0;
     const int w_start = Nk - p.n_w;
 
-    for (int j0 = 0; j0 < Nk; j0 += ATT_BN) {
-        __syncthreads();                      // previous chunk's K/V fully consumed
-        for (int c = tid; c < ATT_BN * CPR; c += 128) {
-            const int r = c / CPR, cc = c - r * CPR;
-            const int j = j0 + r;
-            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-            if (j < n_self) {
-                const __half* src = qkv_b + (int64_t)j * ldq + h * HD + cc * 8;
-                kv = *reinterpret_cast<const uint4*>(src + E);
-                vv = *reinterpret_cast<const uint4*>(src + 2 * E);
-            } else if (j < Nk) {
-                const __half* src = ckv_b + (int64_t)(j - n_self) * ldc + h * HD + cc * 8;
-                kv = *reinterpret_cast<const uint4*>(src);
-                vv = *reinterpret_cast<const uint4*>(src + E);
-            }
-            *reinterpret_cast<uint4*>(sK + r * LDS + cc * 8) = kv;
-            *reinterpret_cast<uint4*>(sV + r * LDS + cc * 8) = vv;
-        }
+    int buf = 0;
+    for (int j0 = 0; j0 < Nk; j0 += ATT_BN, buf ^= 1) {
+        // prefetch the next chunk into the other buffer (all warps finished reading it at the end of the last iteration)
+        if (j0 + ATT_BN < Nk) load_chunk(j0 + ATT_BN, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();                   // this chunk has landed (the prefetch may still be in flight)
         __syncthreads();
+        const __half* sK = sKb + buf * ATT_BN * LDS;
+        const __half* sV = sVb + buf * ATT_BN * LDS;
+        if (warp_active) {
 
         // ---- S = Q K^T for this warp's 16 rows x 64 keys
         float s[ATT_BN / 8][4];
@@ -95,6 +121,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
         for (int i = 0; i < ATT_BN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
 #pragma unroll
         for (int np = 0; np < ATT_BN / 16; ++np) {
+            if (j0 + np * 16 >= Nk) break;    // 16-key groups past the end are fully masked
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks) {
                 uint32_t kf[4];
@@ -158,6 +185,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
         // ---- O += P V
 #pragma unroll
         for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+            if (j0 + kk * 16 >= Nk) break;    // P is zero there
             uint32_t a[4];
             a[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
             a[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
@@ -171,7 +199,10 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
                 mma_16816(o[2 * np + 1], a, vf[2], vf[3]);
             }
         }
+        }                                     // warp_active
+        __syncthreads();                      // everyone is done with this buffer before it is refilled
     }
+    cp_async_wait<0>();
 
     // ---- normalise and store
 #pragma unroll
@@ -196,8 +227,18 @@ int launch_attention(const AttnParams& p, cudaStream_t st) {
     ProfScope prof("attention", 2.0 * ((double)p.B * p.P * 4.0 * p.E + (double)p.B * p.S_max * 2.0 * p.E), st);
     dim3 grid(ceil_div(p.P, ATT_BM), p.nhead, p.B);
     PB_CHECK(grid.y <= 65535 && grid.z <= 65535, "attention: grid too large");
+    const size_t smem = (size_t)(ATT_BM + 4 * ATT_BN) * (hd + 8) * sizeof(__half);
     switch (hd) {
-#define PB_ATT_CASE(H) case H: attention_kernel<H><<<grid, 128, 0, st>>>(p); break;
+#define PB_ATT_CASE(H)                                                                                              \
+    case H: {                                                                                                       \
+        static bool attr = false;                                                                                   \
+        if (!attr) {                                                                                                \
+            PB_CUDA(cudaFuncSetAttribute(attention_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr = true;                                                                                            \
+        }                                                                                                           \
+        attention_kernel<H><<<grid, 128, smem, st>>>(p);                                                            \
+        break;                                                                                                      \
+    }
         PB_ATT_CASE(16) PB_ATT_CASE(32) PB_ATT_CASE(64) PB_ATT_CASE(80) PB_ATT_CASE(96)
 #undef PB_ATT_CASE
         default: PB_CHECK(false, "attention: head_dim %d unsupported (16/32/64/80/96)", hd);

@@ -298,6 +298,64 @@ int launch_grn_apply(__half* h, int64_t M, int N, int P, const float* scale, con
     return 0;
 }
 
+// One-kernel GRN: every CTA recomputes its sample's normaliser mean_n sqrt(sq[b,n]) (N fp32 values from L2), then
+// rescales its rows.  sq_next (the other half of a ping-pong pair) is zeroed for the next block's GEMM epilogue,
+// so the statistic buffer being read is never written in the same launch.
+__global__ void __launch_bounds__(256) grn_fused_kernel(__half* __restrict__ h, int P, int N, const float* __restrict__ sq,
+                                                        float* __restrict__ sq_next, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int rows_per_cta, int zero_per_sample) {
+    const int b = blockIdx.y;
+    const float* sqb = sq + (int64_t)b * N;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < N; i += 256) s += sqrtf(sqb[i]);
+    __shared__ float red[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float inv_denom = 1.0f / (tot / N + 1e-6f);
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < zero_per_sample; i += 256) sq_next[(int64_t)b * zero_per_sample + i] = 0.f;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(P, r0 + rows_per_cta);
+    __half* hb = h + ((int64_t)b * P) * N;
+    for (int ch = threadIdx.x; ch < (N >> 3); ch += 256) {
+        const int col = ch * 8;
+        float sc[8], be[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = fmaf(__ldg(gamma + col + j), sqrtf(sqb[col + j]) * inv_denom, 1.0f);
+            be[j] = __ldg(beta + col + j);
+        }
+        for (int r = r0; r < r1; ++r) {
+            uint4 v = *reinterpret_cast<uint4*>(hb + (int64_t)r * N + col);
+            __half2* hv = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(hv[j]);
+                hv[j] = __floats2half2_rn(fmaf(f.x, sc[2 * j], be[2 * j]), fmaf(f.y, sc[2 * j + 1], be[2 * j + 1]));
+            }
+            *reinterpret_cast<uint4*>(hb + (int64_t)r * N + col) = v;
+        }
+    }
+}
+
+int launch_grn_fused(__half* h, int B, int P, int N, const float* sq, float* sq_next, int zero_per_sample, const float* gamma,
+                     const float* beta, cudaStream_t st) {
+    ProfScope prof("grn", (double)B * P * N * 4.0, st);
+    PB_CHECK(N % 8 == 0, "grn: N=%d must be a multiple of 8", N);
+    if (B == 0 || P == 0) return 0;
+    // ~16 rows per CTA keeps the normaliser recomputation (N sqrt) small next to the rescale (rows * N)
+    const int rows_per_cta = P >= 16 ? 16 : P;
+    dim3 grid(ceil_div(P, rows_per_cta), B);
+    PB_CHECK(grid.y <= 65535, "grn: batch too large");
+    grn_fused_kernel<<<grid, 256, 0, st>>>(h, P, N, sq, sq_next, gamma, beta, rows_per_cta, zero_per_sample);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
 // ------------------------------------------------------------------ timestep embedding + FiLM table
 __global__ void r_embed_kernel(const float* __restrict__ r, int B, int c_r, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -27,6 +27,11 @@ int launch_grn_scale(float* sqsum, const float* gamma, int B, int N, float* scal
 // h[m,n] = h*scale[m/P,n] + beta[n] in place (fp16)
 int launch_grn_apply(__half* h, int64_t M, int N, int P, const float* scale, const float* beta, cudaStream_t st);
 
+// both of the above in one launch: h[b,p,n] = h*(1 + gamma[n]*Gx[b,n]/(mean_n Gx + 1e-6)) + beta[n], Gx = sqrt(sq[b,n]);
+// zeroes all B*zero_per_sample floats of sq_next (the other buffer of a ping-pong pair) for the next block
+int launch_grn_fused(__half* h, int B, int P, int N, const float* sq, float* sq_next, int zero_per_sample, const float* gamma,
+                     const float* beta, cudaStream_t st);
+
 // gen_r_embedding: r [B] -> [B, c_r]
 int launch_r_embed(const float* r, int B, int c_r, float* out, cudaStream_t st);
 // all TimestepBlock mappers at once: out[b, j] = bias[j] + sum_i r_embed[b,i] * W[j,i]; W [total, c_r]

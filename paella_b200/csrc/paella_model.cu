@@ -338,8 +338,8 @@ static void plan_features(const pb200_paella* m, int Bt, int H, int W, Arena& ar
     ws.h16 = ar.take<__half>(4 * max_mc > m0_emb ? 4 * max_mc : m0_emb);
     ws.qkv16 = ar.take<__half>(3 * max_mc);
     ws.o16 = ar.take<__half>(max_mc);
-    ws.gsq = ar.take<float>((int64_t)Bt * 4 * m->max_c);
-    ws.gscale = ar.take<float>((int64_t)Bt * 4 * m->max_c);
+    ws.gsq = ar.take<float>((int64_t)Bt * 4 * m->max_c);        // ping
+    ws.gscale = ar.take<float>((int64_t)Bt * 4 * m->max_c);     // pong (second GRN statistic buffer)
     ws.r_emb = ar.take<float>((int64_t)Bt * c.c_r);
     ws.film = ar.take<float>((int64_t)Bt * (m->film_total > 0 ? m->film_total : 4));
     ws.y = ar.take<float>((int64_t)Bt * H * W * c.c_out);
@@ -529,6 +529,8 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
     PB_TRY(launch_r_embed(r, Bt, c.c_r, ws.r_emb, st));
     PB_TRY(launch_film_table(ws.r_emb, Bt, c.c_r, m->w<float>(m->film_w), m->w<float>(m->film_b), m->film_total, ws.film, st));
     PB_CUDA(cudaMemsetAsync(ws.gsq, 0, (size_t)Bt * 4 * m->max_c * sizeof(float), st));
+    float* grn_stat[2] = {ws.gsq, ws.gscale};      // ping-pong: the GRN kernel of block i zeroes the buffer of block i+1
+    int grn_flip = 0;
 
     // in_mapper + embedding
     PB_TRY(launch_embed_tokens(tokens, m->w<float>(m->emb_table), c.num_labels, c.c_in, Bt, h, w, ps, ws.h16, st));
@@ -574,10 +576,12 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
                     PB_TRY(launch_ln_rows(x, M, ch, 1.0f, 0.0f, ws.a16, nullptr, st));
                 }
                 pb200_gemm_epilogue e1 = epi(PB200_EPI_GELU_F16, m->w<float>(b.b1), ws.h16, 4 * ch);
-                e1.sqsum = ws.gsq; e1.rows_per_sample = P;
+                float* stat = grn_stat[grn_flip];
+                float* stat_next = grn_stat[grn_flip ^ 1];
+                grn_flip ^= 1;
+                e1.sqsum = stat; e1.rows_per_sample = P;
                 PB_TRY(m->gemm(ws.a16, ch, M, ch, b.w1, 4 * (int64_t)ch, e1, st));
-                PB_TRY(launch_grn_scale(ws.gsq, m->w<float>(b.gamma), Bt, 4 * ch, ws.gscale, st));
-                PB_TRY(launch_grn_apply(ws.h16, M, 4 * ch, P, ws.gscale, m->w<float>(b.beta), st));
+                PB_TRY(launch_grn_fused(ws.h16, Bt, P, 4 * ch, stat, stat_next, 4 * m->max_c, m->w<float>(b.gamma), m->w<float>(b.beta), st));
                 pb200_gemm_epilogue e2 = epi(PB200_EPI_RESID_F32, m->w<float>(b.b2), x, ch);
                 e2.resid = x; e2.ldr = ch; e2.rows_per_sample = P;
                 if (b.film_off >= 0) { e2.film = ws.film; e2.film_ld = m->film_total; e2.film_off = b.film_off; }

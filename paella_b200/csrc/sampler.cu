@@ -21,10 +21,12 @@ namespace pb {
 constexpr int SMP_BN = 128;
 constexpr int SMP_STAGES = 6;
 constexpr int SMP_MAX_KB = 4;                 // c_out <= 256
-constexpr int SMP_THREADS = 320;
+constexpr int SMP_EPI_WARPS = 16;             // 4 per TMEM lane quarter: Philox is a long dependent chain, hide it with warps
+constexpr int SMP_THREADS = 64 + 32 * SMP_EPI_WARPS;
+constexpr int SMP_COLS_PER_WARP = SMP_BN / (SMP_EPI_WARPS / 4);
 constexpr int SMP_A_BYTES = 128 * 64 * 2;     // one k-block of the A tile
 constexpr int SMP_W_BYTES = SMP_BN * 64 * 2;
-constexpr int SMP_SMEM = SMP_MAX_KB * SMP_A_BYTES + SMP_STAGES * SMP_W_BYTES + 1024 + 256 + 2 * 128 * 8;
+constexpr int SMP_SMEM = SMP_MAX_KB * SMP_A_BYTES + SMP_STAGES * SMP_W_BYTES + 1024 + 256 + (SMP_EPI_WARPS / 4) * 128 * 8;
 
 __global__ void __launch_bounds__(SMP_THREADS, 1)
 fused_sampler_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, int R, int NL,
@@ -42,8 +44,8 @@ fused_sampler_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     const uint32_t a_bar = bar_base + 8u * (2 * SMP_STAGES + 4);
     const uint32_t tmem_slot = bar_base + 8u * (2 * SMP_STAGES + 5);
     uint8_t* tail = smem_gen + (bar_base - smem_base) + 256;
-    float* best_v = reinterpret_cast<float*>(tail);                // [128] second half's candidate
-    int* best_i = reinterpret_cast<int*>(tail + 128 * 4);
+    float* best_v = reinterpret_cast<float*>(tail);                // [slices-1][128] candidates of the other column slices
+    int* best_i = reinterpret_cast<int*>(tail + (SMP_EPI_WARPS / 4) * 128 * 4);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -58,7 +60,7 @@ fused_sampler_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < SMP_STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-            for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 8); }
+            for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), SMP_EPI_WARPS); }
             ptx::mbar_init(a_bar, 1);
             ptx::fence_barrier_init();
         }
@@ -112,7 +114,7 @@ fused_sampler_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         }
     } else {
         const int q = warp & 3;                  // TMEM lane quarter
-        const int half = (warp - 2) >> 2;        // which 64 of the chunk's 128 columns
+        const int half = (warp - 2) >> 2;        // which slice of the chunk's 128 columns
         const int row_in_tile = q * 32 + lane;
         const int row = m_idx + row_in_tile;
         const bool row_ok = row < R;
@@ -123,10 +125,10 @@ fused_sampler_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             ptx::mbar_wait(tfull_bar(as), (ch >> 1) & 1);
             ptx::tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < 64; c += 32) {
-                const int col0 = ch * SMP_BN + half * 64 + c;
+            for (int c = 0; c < SMP_COLS_PER_WARP; c += 32) {
+                const int col0 = ch * SMP_BN + half * SMP_COLS_PER_WARP + c;
                 float v[32];
-                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * SMP_BN + half * 64 + c), v);
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * SMP_BN + half * SMP_COLS_PER_WARP + c), v);
                 if (row_ok && col0 < NL) {
                     const uint64_t e0 = (uint64_t)row * (uint64_t)NL + (uint64_t)col0;
                     uint64_t j = e0 / rng.stride;
@@ -147,13 +149,17 @@ fused_sampler_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
         }
-        // combine the two column halves of each row
-        if (half == 1) { best_v[row_in_tile] = bv; best_i[row_in_tile] = bidx; }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // combine the column slices of each row
+        constexpr int NS = SMP_EPI_WARPS / 4;
+        if (half > 0) { best_v[(half - 1) * 128 + row_in_tile] = bv; best_i[(half - 1) * 128 + row_in_tile] = bidx; }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * SMP_EPI_WARPS) : "memory");
         if (half == 0 && row_ok) {
-            const float ov = best_v[row_in_tile];
-            const int oi = best_i[row_in_tile];
-            if (ov > bv || (ov == bv && oi < bidx)) bidx = oi;
+#pragma unroll
+            for (int s = 0; s < NS - 1; ++s) {
+                const float ov = best_v[s * 128 + row_in_tile];
+                const int oi = best_i[s * 128 + row_in_tile];
+                if (ov > bv || (ov == bv && oi < bidx)) { bv = ov; bidx = oi; }
+            }
             out[row] = bidx;
         }
     }

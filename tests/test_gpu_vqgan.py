@@ -52,7 +52,8 @@ def test_tiny_encode_latents_and_indices(tiny):
     # indices: bit-exact given OUR latents (channels-last vectors), through the C oracle
     want = vo.vq_nearest(lat.permute(0, 2, 3, 1).reshape(-1, 4).contiguous(), sd["vquantizer.codebook.weight"]).view(idx.shape)
     assert torch.equal(idx.cpu(), want)
-    assert torch.equal((qe * m.scale_factor).cpu(), sd["vquantizer.codebook.weight"][idx.cpu()].permute(0, 3, 1, 2))
+    torch.testing.assert_close((qe * m.scale_factor).cpu(), sd["vquantizer.codebook.weight"][idx.cpu()].permute(0, 3, 1, 2),
+                               rtol=1e-6, atol=1e-7)        # (x / sf) * sf round trip
     # notebook calls encode(x, quantize=True)
     assert torch.equal(m.encode(img, quantize=True)[2], idx)
 
@@ -117,8 +118,8 @@ def test_f4_roundtrip_vs_oracle(f4):
     assert lat_err < 2e-2
     assert agree > 0.98 and worst < 5e-2
     # north_star: decoded RGB within 1e-3 abs of fp32.  fp16 operands + fp32 accumulation predict 8.4e-4 max on this
-    # input (oracle with fp16-rounded operands); bound at 2e-3, measured value logged to gpurun_out/vqgan_parity.jsonl.
-    assert dec_err < 2e-3
+    # input (oracle with fp16-rounded operands); measured on B200: 7.4e-4 (profiles/r01_vqgan_parity.jsonl).
+    assert dec_err < 1e-3
 
 
 def test_f4_large_batch_roundtrip_properties(f4):
@@ -133,7 +134,8 @@ def test_f4_large_batch_roundtrip_properties(f4):
     b = m.decode_indices(idx)
     assert torch.equal(a, b)                       # no atomics on this path: bit-reproducible
     assert a.shape == (16, 3, 256, 256) and bool(torch.isfinite(a).all())
-    # decode(latents) == decode_indices(indices) when the latents are the codebook rows
+    # decode(latents) ~= decode_indices(indices) when the latents are the codebook rows: (z / sf) * sf moves the
+    # latents by an ulp, which flips fp16 operand roundings downstream -> same size as the fp16 error itself
     z = m.vquantizer.idx2vq(idx, dim=1) / m.scale_factor
     c = m.decode(z)
-    assert float((c - a).abs().max()) < 1e-5
+    assert float((c - a).abs().max()) < 2e-3
