@@ -80,12 +80,14 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // rounding of the stored activation), one MUFU.RCP + one MUFU.EX2 + 7 FMA instead of libdevice erff's branches.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));        // 1 ulp-ish, one MUFU
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));     // exp(-z^2), one MUFU
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    const float erfc_abs = p * t * exp2f(-1.4426950408889634f * z * z);     // erfc(|x|/sqrt2)
+    const float erfc_abs = p * t * e;                                                    // erfc(|x|/sqrt2)
     const float cdf = x >= 0.f ? 1.0f - 0.5f * erfc_abs : 0.5f * erfc_abs;   // Phi(x)
     return x * cdf;
 }

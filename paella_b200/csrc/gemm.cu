@@ -14,6 +14,8 @@
 //              overlaps with the next tile's MMAs through the second TMEM buffer.
 #include "gemm.cuh"
 
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <unordered_map>
 
@@ -222,7 +224,7 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
 // (im2col-free convolution): a 128-row tile is a th x tw patch of the output grid and k-block kb selects a filter
 // tap and a 64-channel slice; out-of-image taps are zero-filled by the TMA unit (the conv's zero padding).
 template <int BLOCK_N, int MODE, int AMODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const pb200_gemm_epilogue ep, const ConvGeom geom, int M, int N, int K) {
     using L = GemmSmem<BLOCK_N>;
@@ -240,8 +242,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int n_tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
     const int n_tiles_m = AMODE == 0 ? (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M : geom.batch * geom.tiles_y * geom.tiles_x;
-    const int n_tiles = n_tiles_m * n_tiles_n;
     const int n_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    // Optional 2-CTA cluster (launch attribute): the two CTAs take M-tiles 2p and 2p+1 of the same N-tile and each
+    // loads only HALF of the W tile, multicasting it into both CTAs' shared memory — the SM<-L2 traffic per FLOP
+    // drops by a third (ncu: the single-CTA kernel saturates the L2->SM fabric at ~13 TB/s).
+    const uint32_t csize = ptx::cluster_nctarank();
+    const uint32_t crank = ptx::cluster_ctarank();
+    const int n_units = ((n_tiles_m + (int)csize - 1) / (int)csize) * n_tiles_n;     // work units = (M-tile group, N-tile)
+    const int unit0 = blockIdx.x / csize, unit_step = gridDim.x / csize;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm_a);
@@ -251,11 +259,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         if (lane == 0) {
             for (int s = 0; s < L::STAGES; ++s) {
                 ptx::mbar_init(full_bar(s), 1);
-                ptx::mbar_init(empty_bar(s), 1);
+                ptx::mbar_init(empty_bar(s), csize);        // every CTA of the cluster must have drained the stage
             }
             for (int s = 0; s < 2; ++s) {
                 ptx::mbar_init(tfull_bar(s), 1);
-                ptx::mbar_init(tempty_bar(s), GEMM_EPI_WARPS);       // one arrival per epilogue warp
+                ptx::mbar_init(tempty_bar(s), gemm_epi_warps(BLOCK_N));       // one arrival per epilogue warp
             }
             ptx::fence_barrier_init();
         }
@@ -266,6 +274,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
+    if (csize > 1) ptx::cluster_sync();          // peer barriers are initialised before anything can signal them
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
@@ -273,10 +282,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int mt = tile / n_tiles_n;
+            for (int unit = unit0; unit < n_units; unit += unit_step) {
+                const int mt = (unit / n_tiles_n) * (int)csize + (int)crank;
                 const int m_idx = mt * GEMM_BLOCK_M;
-                const int n_idx = (tile % n_tiles_n) * BLOCK_N;
+                const int n_idx = (unit % n_tiles_n) * BLOCK_N;
                 int cb = 0, cy0 = 0, cx0 = 0;
                 if (AMODE != 0) {
                     cb = mt / (geom.tiles_y * geom.tiles_x);
@@ -306,7 +315,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         const int ox = geom.px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0);
                         ptx::tma_load_4d(&tm_a, full_bar(stage), sa, cc * 64, cx0 + ox, cy0 + oy, cb);
                     }
-                    ptx::tma_load_2d(&tm_b, full_bar(stage), sa + L::A_BYTES, kb * GEMM_BLOCK_K, n_idx);
+                    if (csize == 1) {          // the W map's box is half a tile (BLOCK_N/2 rows): two loads
+                        ptx::tma_load_2d(&tm_b, full_bar(stage), sa + L::A_BYTES, kb * GEMM_BLOCK_K, n_idx);
+                        ptx::tma_load_2d(&tm_b, full_bar(stage), sa + L::A_BYTES + L::B_BYTES / 2, kb * GEMM_BLOCK_K,
+                                         n_idx + BLOCK_N / 2);
+                    } else {   // my half of the W tile, written into both CTAs' stage (same offsets, same barrier slot)
+                        ptx::tma_load_2d_mcast(&tm_b, full_bar(stage), sa + L::A_BYTES + crank * (L::B_BYTES / 2),
+                                               kb * GEMM_BLOCK_K, n_idx + (int)crank * (BLOCK_N / 2), (uint16_t)0x3);
+                    }
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -317,7 +333,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         int iter = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+        for (int unit = unit0; unit < n_units; unit += unit_step, ++iter) {
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
             ptx::mbar_wait(tempty_bar(as), aphase ^ 1);
@@ -335,7 +351,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in (addr>>4)
                         ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs retire
+                    if (csize == 1) ptx::umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+                    else ptx::umma_commit_mcast(empty_bar(stage), (uint16_t)0x3);   // ... in both CTAs of the pair
                     if (kb == n_kb - 1) ptx::umma_commit(tfull_bar(as)); // accumulator complete
                 }
                 __syncwarp();
@@ -346,14 +363,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         // ===================== epilogue =====================
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int half = (warp - 2) >> 2;       // which half of the tile's columns (two warps share a quarter)
-        constexpr int COLS_PER_WARP = BLOCK_N / (GEMM_EPI_WARPS / 4);
+        constexpr int COLS_PER_WARP = BLOCK_N / (gemm_epi_warps(BLOCK_N) / 4);
         int iter = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+        for (int unit = unit0; unit < n_units; unit += unit_step, ++iter) {
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
-            const int mt = tile / n_tiles_n;
+            const int mt = (unit / n_tiles_n) * (int)csize + (int)crank;
             const int m_idx = mt * GEMM_BLOCK_M;
-            const int n_idx = (tile % n_tiles_n) * BLOCK_N;
+            const int n_idx = (unit % n_tiles_n) * BLOCK_N;
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
             int row = m_idx + q * 32 + lane;
@@ -381,6 +398,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (csize > 1) ptx::cluster_sync();          // the peer may still be multicasting into / signalling this CTA
     if (warp == 1) ptx::tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
@@ -399,9 +417,27 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_
     memset(&g, 0, sizeof(g));
     if (geom) g = *geom;
     const int tiles_m = AMODE == 0 ? ceil_div(M, GEMM_BLOCK_M) : g.batch * g.tiles_y * g.tiles_x;
-    const int n_tiles = tiles_m * ceil_div(N, BLOCK_N);
-    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    gemm_f16_kernel<BLOCK_N, MODE, AMODE><<<grid, GEMM_THREADS, L::SMEM_BYTES, st>>>(ta, tb, ep, g, M, N, K);
+    const int tiles_n = ceil_div(N, BLOCK_N);
+    // pairs of CTAs (one cluster) share the W tile through TMA multicast when there are >= 2 M-tiles
+    static const bool no_cluster = getenv("PB200_NO_CLUSTER") != nullptr;
+    const int csize = (AMODE == 0 && tiles_m >= 2 && !no_cluster) ? 2 : 1;
+    const int n_units = ceil_div(tiles_m, csize) * tiles_n;
+    const int max_clusters = sm_count() / csize;
+    const int grid = csize * (n_units < max_clusters ? n_units : max_clusters);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(gemm_threads(BLOCK_N));
+    cfg.dynamicSmemBytes = L::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_kernel<BLOCK_N, MODE, AMODE>, ta, tb, ep, g, M, N, K));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -489,7 +525,7 @@ int gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, 
     const int bn = gemm_pick_block_n(M, N);
     CUtensorMap ta, tb;
     PB_TRY(make_tmap_f16_2d(&ta, a, M, K, lda, GEMM_BLOCK_M));
-    PB_TRY(make_tmap_f16_2d(&tb, w, N, K, ldw, bn));
+    PB_TRY(make_tmap_f16_2d(&tb, w, N, K, ldw, bn / 2));      // W box = half a tile (see the producer)
     return gemm_launch(ta, tb, bn, ep, M, N, K, st);
 }
 

@@ -8,8 +8,10 @@ namespace pb {
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;     // 64 fp16 = one 128-byte swizzle row
-constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes half of the tile's columns
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;    // TMA warp, MMA warp, epilogue warps
+// Epilogue warps: several per TMEM lane quarter, each taking a slice (>= 32 columns) of the tile's columns.  The
+// epilogue is a latency-bound instruction stream (ncu: IPC 1.4 with 8 warps), so it gets as many warps as columns allow.
+constexpr int gemm_epi_warps(int block_n) { return block_n >= 128 ? 16 : 8; }
+constexpr int gemm_threads(int block_n) { return 64 + 32 * gemm_epi_warps(block_n); }   // + TMA warp + MMA warp
 
 template <int BLOCK_N>
 struct GemmSmem {

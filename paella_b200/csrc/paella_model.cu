@@ -146,7 +146,7 @@ struct pb200_paella {
         const int bn = gemm_pick_block_n(M, N);
         const CUtensorMap *ta, *tb;
         PB_TRY(tmap(A, M, K, lda, GEMM_BLOCK_M, &ta));
-        PB_TRY(tmap(w<__half>(w_off), N, K, K, bn, &tb));
+        PB_TRY(tmap(w<__half>(w_off), N, K, K, bn / 2, &tb));     // W box = half a tile
         return gemm_launch(*ta, *tb, bn, ep, M, N, K, st);
     }
 };

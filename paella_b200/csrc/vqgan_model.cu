@@ -272,7 +272,7 @@ struct pb200_vqgan {
         const int bn = gemm_pick_block_n(M, N);
         const CUtensorMap *ta, *tb;
         PB_TRY(tmap2d(A, M, K, lda, GEMM_BLOCK_M, &ta));
-        PB_TRY(tmap2d(w<__half>(w_off), N, K, K, bn, &tb));
+        PB_TRY(tmap2d(w<__half>(w_off), N, K, K, bn / 2, &tb));     // W box = half a tile
         return gemm_launch(*ta, *tb, bn, ep, M, N, K, st);
     }
 };
@@ -455,7 +455,7 @@ int pb200_vqgan_encode(pb200_vqgan* m, const float* img, int batch, int img_h, i
         const int box[5] = {64, g.tw, 1, g.th, 1};
         PB_TRY(make_tmap_f16_nd(&ta, ws.a16, 5, dims, strides, box));
         const CUtensorMap* tb;
-        PB_TRY(m->tmap2d(m->w<__half>(m->down_w), N, K, K, bn, &tb));
+        PB_TRY(m->tmap2d(m->w<__half>(m->down_w), N, K, K, bn / 2, &tb));
         pb200_gemm_epilogue e = vepi(PB200_EPI_F32, m->w<float>(m->down_b), ws.xb, c1);
         PB_TRY(gemm_conv_launch(ta, *tb, bn, e, g, N, K, st));
     }
@@ -521,7 +521,7 @@ int pb200_vqgan_decode(pb200_vqgan* m, const int64_t* indices, const float* late
         for (int ph = 0; ph < 4; ++ph) {
             g.py = ph >> 1; g.px = ph & 1;
             const CUtensorMap* tb;
-            PB_TRY(m->tmap2d(m->w<__half>(m->up_w) + (int64_t)ph * N * K, N, K, K, bn, &tb));
+            PB_TRY(m->tmap2d(m->w<__half>(m->up_w) + (int64_t)ph * N * K, N, K, K, bn / 2, &tb));
             pb200_gemm_epilogue e = vepi(PB200_EPI_F32, m->w<float>(m->up_b), ws.xa, c0);
             PB_TRY(gemm_conv_launch(ta, *tb, bn, e, g, N, K, st));
         }
