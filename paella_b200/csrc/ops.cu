@@ -132,16 +132,16 @@ int launch_ln_patchify2(const float* x, int B, int h, int w, int c, __half* out,
 // ------------------------------------------------------------------ depthwise conv + LayerNorm (warp per position)
 // NV = float4 chunks per lane: supports c <= NV*128.
 template <int NV, bool SKIP>
-__global__ void __launch_bounds__(512) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ skip,
+__global__ void __launch_bounds__(128) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ skip,
                                                         const float* __restrict__ wp, const float* __restrict__ bias,
                                                         int B, int h, int w, int c, int k, __half* __restrict__ out) {
-    // one CTA = a 4x4 patch of positions of one sample (16 warps): the 3x3 halos overlap, so the 144 tap rows the
-    // patch reads are only 36 distinct rows — served by L1 instead of 9 L2 reads per position
+    // one CTA = a 2x2 patch of positions of one sample (4 warps, small CTAs for occupancy: measured on B200, 16-warp
+    // 4x4 patches were 18% slower); the four 3x3 halos overlap so half of the tap rows come from L1
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int pw = (w + 3) >> 2, ph = (h + 3) >> 2;
+    const int pw = (w + 1) >> 1, ph = (h + 1) >> 1;
     const int b = blockIdx.x / (pw * ph);
     const int pr = blockIdx.x - b * (pw * ph);
-    const int y = (pr / pw) * 4 + (wid >> 2), xx = (pr % pw) * 4 + (wid & 3);
+    const int y = (pr / pw) * 2 + (wid >> 1), xx = (pr % pw) * 2 + (wid & 1);
     if (y >= h || xx >= w) return;
     const int64_t pos = ((int64_t)b * h + y) * w + xx;
     const int nvq = c >> 2;          // float4 chunks in a row
@@ -223,12 +223,12 @@ __global__ void __launch_bounds__(512) dwconv_ln_kernel(const float* __restrict_
 template <int NV>
 static int dwconv_dispatch(const float* x, const float* skip, const float* wp, const float* bias, int B, int h, int w,
                            int c, int k, __half* out, cudaStream_t st) {
-    const int64_t grid = (int64_t)B * ((h + 3) / 4) * ((w + 3) / 4);
+    const int64_t grid = (int64_t)B * ((h + 1) / 2) * ((w + 1) / 2);
     PB_CHECK(grid < (1ll << 31), "dwconv: grid too large");
     if (skip)
-        dwconv_ln_kernel<NV, true><<<(unsigned)grid, 512, 0, st>>>(x, skip, wp, bias, B, h, w, c, k, out);
+        dwconv_ln_kernel<NV, true><<<(unsigned)grid, 128, 0, st>>>(x, skip, wp, bias, B, h, w, c, k, out);
     else
-        dwconv_ln_kernel<NV, false><<<(unsigned)grid, 512, 0, st>>>(x, skip, wp, bias, B, h, w, c, k, out);
+        dwconv_ln_kernel<NV, false><<<(unsigned)grid, 128, 0, st>>>(x, skip, wp, bias, B, h, w, c, k, out);
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -311,7 +311,10 @@ __global__ void __launch_bounds__(256) grn_fused_kernel(__half* __restrict__ h, 
     const int b = blockIdx.y;
     const float* sqb = sq + (int64_t)b * N;
     float s = 0.f;
-    for (int i = threadIdx.x; i < N; i += 256) s += sqrtf(sqb[i]);
+    for (int i = threadIdx.x; i < (N >> 2); i += 256) {
+        const float4 q = *reinterpret_cast<const float4*>(sqb + 4 * i);
+        s += (sqrtf(q.x) + sqrtf(q.y)) + (sqrtf(q.z) + sqrtf(q.w));
+    }
     __shared__ float red[8];
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -328,10 +331,18 @@ __global__ void __launch_bounds__(256) grn_fused_kernel(__half* __restrict__ h, 
     for (int ch = threadIdx.x; ch < (N >> 3); ch += 256) {
         const int col = ch * 8;
         float sc[8], be[8];
+        {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+            const float4 q0 = *reinterpret_cast<const float4*>(sqb + col), q1 = *reinterpret_cast<const float4*>(sqb + col + 4);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            sc[j] = fmaf(__ldg(gamma + col + j), sqrtf(sqb[col + j]) * inv_denom, 1.0f);
-            be[j] = __ldg(beta + col + j);
+            for (int j = 0; j < 8; ++j) {
+                sc[j] = fmaf(gg[j], sqrtf(qq[j]) * inv_denom, 1.0f);
+                be[j] = bb[j];
+            }
         }
         for (int r = r0; r < r1; r += 8) {       // 8 independent 16-byte loads in flight per thread
             uint4 v[8];

@@ -431,7 +431,9 @@ int64_t pb200_paella_workspace_bytes(const pb200_paella* m, int batch_total, int
     CondWs cw;
     plan_cond(m, batch_total, s_max, s_max, b, cw);
     // logits / sampling scratch: fp16 features for B*H*W rows
-    const int64_t samp = ((int64_t)batch_total * h * w * m->cfg.c_out * 2 + 255) / 256 * 256;
+    // fp16 features of the sampler; the shared-Philox kernel reads whole 4*rs-row blocks (rs <= 1184*256/num_labels + 1)
+    const int64_t pad_rows = 4 * ((int64_t)1184 * 256 / m->cfg.num_labels + 2);
+    const int64_t samp = (((int64_t)batch_total * h * w + pad_rows) * m->cfg.c_out * 2 + 255) / 256 * 256;
     int64_t need = a.off > b.off ? a.off : b.off;
     need = need > samp ? need : samp;
     return need + 256;
@@ -646,7 +648,8 @@ int pb200_paella_sample_tokens(pb200_paella* m, const float* features, int batch
     const pb200_paella_config& c = m->cfg;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t rows = (int64_t)batch * hw;
-    PB_CHECK(rows * c.c_out * 2 <= workspace_bytes, "sample_tokens: workspace too small");
+    PB_CHECK(fused_sampler_rows_padded(rows, c.num_labels) * c.c_out * 2 <= workspace_bytes,
+             "sample_tokens: workspace too small (use pb200_paella_workspace_bytes)");
     PB_CHECK(temperature > 0, "sample_tokens: temperature must be positive");
     __half* a16 = reinterpret_cast<__half*>(workspace);
     // classifier-free guidance is linear in the features: mix before the GEMM

@@ -372,7 +372,7 @@ class Paella(nn.Module):
         dev = self._device()
         with torch.cuda.device(dev):
             out = torch.empty(batch, h, w, dtype=torch.int64, device=dev)
-            ws = self._ws(batch * h * w * self._cfg["c_out"] * 2 + 256)
+            ws = self._ws(L.pb200_paella_workspace_bytes(self._handle, batch, h, w, 1))
             seed, off = ops.take_philox(batch * h * w * self.num_labels, dev, generator)
             check(L.pb200_paella_sample_tokens(self._handle, ptr(feats), batch, h * w, 1 if cfg is not None else 0,
                                                float(cfg) if cfg is not None else 0.0, float(temperature), seed, off,

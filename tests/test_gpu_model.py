@@ -98,26 +98,30 @@ def test_cpu_tensors_are_refused():
         m(t(g["x"]), t(g["r"]), t(g["byt5"]))
 
 
-def test_fused_sampler_matches_torch_multinomial():
-    """out_mapper GEMM + CFG + /T + multinomial in one kernel vs the same expression in torch ops, same seed."""
+@pytest.mark.parametrize("NL,B,H", [(8192, 8, 32), (8192, 3, 8), (8200, 2, 16), (64, 2, 8), (8192, 64, 32)])
+def test_fused_sampler_matches_torch_multinomial(NL, B, H):
+    """out_mapper GEMM + CFG + /T + multinomial in one kernel vs the same expression in torch ops, same seed.
+    (8192, B=8/64) = full-grid torch launch policy (stride 37*8192: shared-Philox kernel, partial last block at B=8);
+    (8192, 3x8x8) and (64, ...) = small-grid policies (rs = rows); 8200 labels = stride not a multiple of the label
+    count -> generic per-element kernel."""
     from paella_b200.modules import Paella
     cfg, sd, g = load_golden("paella_tiny.npz")
     big = dict(cfg)
-    big.update(c_in=256, c_out=256, num_labels=8192)
+    big.update(c_in=256, c_out=256, num_labels=NL)
     torch.manual_seed(0)
     m = Paella(**big).to(DEV).eval()
-    B, H = 8, 32
     gen = torch.Generator(device=DEV).manual_seed(3)
     feats = torch.randn(2 * B * H * H, 256, device=DEV, generator=gen)
-    W = m.out_mapper[1].weight.detach().view(8192, 256) * 30.0        # spread the logits
+    W = m.out_mapper[1].weight.detach().view(NL, 256) * 30.0        # spread the logits
     with torch.no_grad():
-        m.out_mapper[1].weight.copy_(W.view(8192, 256, 1, 1))
+        m.out_mapper[1].weight.copy_(W.view(NL, 256, 1, 1))
     m.pack_weights()
     n = B * H * H
     cfg_s, T = 8.0, 0.7
     a_mix = (feats[:n] * cfg_s + feats[n:] * (1 - cfg_s)).half().float()
     logits = a_mix @ W.half().float().t()
     p = torch.softmax(logits / T, dim=-1)
+    del logits
     torch.manual_seed(42)
     want = torch.multinomial(p, 1)[:, 0].view(B, H, H)
     off_a = torch.cuda.default_generators[0].get_offset()
@@ -125,11 +129,10 @@ def test_fused_sampler_matches_torch_multinomial():
     got = m.sample_tokens(feats, B, H, H, cfg_s, T)
     assert torch.cuda.default_generators[0].get_offset() == off_a
     agree = float((got == want).float().mean())
-    # disagreements must be near-ties of p/q
-    bad = (got != want).view(-1).nonzero().flatten()
-    _log("fused_sampler", {"agree": agree, "n": n, "mismatch": int(bad.numel())})
+    _log("fused_sampler", {"NL": NL, "B": B, "H": H, "agree": agree, "n": n, "mismatch": int((got != want).sum())})
     assert agree > 0.999
     # no guidance
+    del p
     torch.manual_seed(43)
     want2 = torch.multinomial(torch.softmax((feats[:n].half().float() @ W.half().float().t()) / T, dim=-1), 1)[:, 0].view(B, H, H)
     torch.manual_seed(43)
