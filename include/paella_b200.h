@@ -104,7 +104,8 @@ typedef struct pb200_gemm_epilogue {
     const float* resid;        /* RESID: fp32 [M, ldr] (may alias out) */
     int64_t ldr;
     float alpha;               /* RESID: scale on (acc+bias); 1.0 for the denoiser */
-    float* sqsum;              /* GELU: fp32 [M/rows_per_sample, N] accumulated with atomics, or NULL */
+    uint64_t* sqsum;           /* GELU: [M/rows_per_sample, N] sum of out^2 in 2^-24 fixed point (integer atomics:
+                                  order-independent, hence run-to-run deterministic), or NULL */
     int rows_per_sample;       /* GELU/RESID(film)/NCHW: rows of one sample */
     const float* film;         /* RESID: fp32 [B, film_ld]: a = film[b, film_off + n], b = film[b, film_off + N + n]; or NULL */
     int64_t film_ld;

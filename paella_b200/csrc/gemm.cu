@@ -135,7 +135,12 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
                     *reinterpret_cast<uint4*>(o + g * 8) = pk;
                 }
         }
-        if (ep.sqsum) {   // GlobalResponseNorm statistic: sum over the sample's positions of h^2, per channel
+        if (ep.sqsum) {   // GlobalResponseNorm statistic: sum over the sample's positions of h^2, per channel.
+            // Accumulated in 2^-24 fixed point with 64-bit integer atomics: integer addition is associative, so the
+            // result does not depend on the order in which warps/CTAs arrive (float atomics made two runs of the same
+            // seed differ in the last bits, which flipped ~2% of the sampled tokens over 8 steps).
+            unsigned long long* sq = reinterpret_cast<unsigned long long*>(ep.sqsum);
+            auto fx = [](float x) { return (unsigned long long)__float2ull_rn(x * 16777216.0f); };
             const int P = ep.rows_per_sample;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (row_ok && col0 + j < N) ? v[j] * v[j] : 0.f;
@@ -153,7 +158,7 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
                 }
                 const int row0 = row - lane;
                 if (row0 < M && col0 + lane < N)
-                    atomicAdd(ep.sqsum + (int64_t)(row0 / P) * N + col0 + lane, v[0]);
+                    atomicAdd(sq + (int64_t)(row0 / P) * N + col0 + lane, fx(v[0]));
             } else if ((P & (P - 1)) == 0 && P < 32) {
                 for (int o = P >> 1; o > 0; o >>= 1) {
 #pragma unroll
@@ -162,12 +167,12 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
                 if (row_ok && (lane & (P - 1)) == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (col0 + j < N) atomicAdd(ep.sqsum + (int64_t)(row / P) * N + col0 + j, v[j]);
+                        if (col0 + j < N) atomicAdd(sq + (int64_t)(row / P) * N + col0 + j, fx(v[j]));
                 }
             } else if (row_ok) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (col0 + j < N) atomicAdd(ep.sqsum + (int64_t)(row / P) * N + col0 + j, v[j]);
+                    if (col0 + j < N) atomicAdd(sq + (int64_t)(row / P) * N + col0 + j, fx(v[j]));
             }
         }
     } else if (MODE == PB200_EPI_RESID_F32) {
@@ -402,6 +407,204 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (warp == 1) ptx::tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------ 2-SM kernel (cta_group::2)
+// A CTA pair (cluster of 2 on one TPC) computes a 256 x BLOCK_N tile with ONE tcgen05.mma.cta_group::2 stream issued
+// by the leader CTA: each CTA stages its own 128 rows of A and only its HALF of the W tile (BLOCK_N/2 rows); the
+// tensor cores of both SMs read both halves.  Per SM this halves the W bytes pulled from L2 and the W bytes read
+// from shared memory per MMA (ncu on the 1-SM kernel: L2->SM fabric at ~13 TB/s and, for BLOCK_N=128, the
+// 128 B/clk shared-memory port are the limiters).  Accumulators: each CTA's TMEM holds its 128 rows x BLOCK_N.
+//   full[s]   (leader)  : 2 arrivals (both producers) + the bytes of both CTAs' TMA loads (cta_group::2 loads
+//                         complete_tx on the leader's barrier)
+//   empty[s]  (each CTA): tcgen05.commit.cta_group::2 multicast from the leader's MMA thread
+//   tfull[a]  (each CTA): same commit, when a tile's last k-block has been issued
+//   tempty[a] (leader)  : one arrival per epilogue warp of BOTH CTAs (the peer arrives remotely)
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1)
+gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                    const pb200_gemm_epilogue ep, int M, int N, int K) {
+    constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+    constexpr int BH_BYTES = (BLOCK_N / 2) * GEMM_BLOCK_K * 2;       // this CTA's half of the W tile
+    constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
+    constexpr int STAGES = BLOCK_N >= 256 ? 6 : 8;
+    constexpr int TMEM_COLS = BLOCK_N >= 256 ? 512 : 256;
+    constexpr int EW = gemm_epi_warps(BLOCK_N);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t crank = ptx::cluster_ctarank();
+    const bool leader = crank == 0;
+    const int n_tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+    const int n_pairs_m = (M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+    const int n_units = n_pairs_m * n_tiles_n;
+    const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
+    const int n_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_a);
+        ptx::prefetch_tensormap(&tm_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                ptx::mbar_init(full_bar(s), 2);
+                ptx::mbar_init(empty_bar(s), 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                ptx::mbar_init(tfull_bar(s), 1);
+                ptx::mbar_init(tempty_bar(s), 2 * EW);
+            }
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc_cg2(tmem_slot, TMEM_COLS);
+        ptx::tmem_relinquish_cg2();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    ptx::cluster_sync();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t leader_full0 = ptx::mapa(full_bar(0), 0);      // leader's full[0] in cluster address space
+            for (int unit = unit0; unit < n_units; unit += unit_step) {
+                const int m_idx = (unit / n_tiles_n) * (2 * GEMM_BLOCK_M) + (int)crank * GEMM_BLOCK_M;
+                const int n_idx = (unit % n_tiles_n) * BLOCK_N + (int)crank * (BLOCK_N / 2);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t lfull = leader_full0 + 8u * stage;
+                    if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+                    else ptx::mbar_arrive_cluster(lfull);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    ptx::tma_load_2d_cg2(&tm_a, lfull, sa, kb * GEMM_BLOCK_K, m_idx);
+                    ptx::tma_load_2d_cg2(&tm_b, lfull, sa + A_BYTES, kb * GEMM_BLOCK_K, n_idx);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            constexpr uint32_t idesc = ptx::umma_idesc_f16(2 * GEMM_BLOCK_M, BLOCK_N, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int unit = unit0; unit < n_units; unit += unit_step, ++iter) {
+                const int as = iter & 1;
+                const uint32_t aphase = (iter >> 1) & 1;
+                ptx::mbar_wait(tempty_bar(as), aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                        const uint64_t da = ptx::umma_desc_kmajor_sw128(sa);
+                        const uint64_t db = ptx::umma_desc_kmajor_sw128(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+                            ptx::umma_f16_cg2(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        ptx::umma_commit_cg2_mcast(empty_bar(stage), (uint16_t)0x3);
+                        if (kb == n_kb - 1) ptx::umma_commit_cg2_mcast(tfull_bar(as), (uint16_t)0x3);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (both CTAs, own 128 rows) =====================
+        const int q = warp & 3;
+        const int slice = (warp - 2) >> 2;
+        constexpr int COLS_PER_WARP = BLOCK_N / (EW / 4);
+        const uint32_t leader_tempty0 = ptx::mapa(tempty_bar(0), 0);
+        int iter = 0;
+        for (int unit = unit0; unit < n_units; unit += unit_step, ++iter) {
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            const int m_idx = (unit / n_tiles_n) * (2 * GEMM_BLOCK_M) + (int)crank * GEMM_BLOCK_M;
+            const int n_idx = (unit % n_tiles_n) * BLOCK_N;
+            ptx::mbar_wait(tfull_bar(as), aphase);
+            ptx::tc_fence_after();
+            const int row = m_idx + q * 32 + lane;
+#pragma unroll 1
+            for (int c = slice * COLS_PER_WARP; c < (slice + 1) * COLS_PER_WARP; c += 32) {
+                if (n_idx + c >= N) break;
+                float v[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c), v);
+                epilogue_chunk<MODE>(ep, M, N, row, n_idx + c, v, lane);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(leader_tempty0 + 8u * as);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 1) ptx::tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+}
+
+template <int BLOCK_N, int MODE>
+static int launch_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_gemm_epilogue& ep, int M, int N, int K,
+                      cudaStream_t st) {
+    constexpr int STAGES = BLOCK_N >= 256 ? 6 : 8;
+    constexpr int SMEM = STAGES * (GEMM_BLOCK_M * 128 + (BLOCK_N / 2) * 128) + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(gemm_f16_cg2_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set = true;
+    }
+    const int n_units = ceil_div(M, 2 * GEMM_BLOCK_M) * ceil_div(N, BLOCK_N);
+    const int max_pairs = sm_count() / 2;
+    const int grid = 2 * (n_units < max_pairs ? n_units : max_pairs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(gemm_threads(BLOCK_N));
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_cg2_kernel<BLOCK_N, MODE>, ta, tb, ep, M, N, K));
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int BLOCK_N>
+static int launch_cg2_mode(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_gemm_epilogue& ep, int M, int N, int K,
+                           cudaStream_t st) {
+    switch (ep.mode) {
+        case PB200_EPI_F16: return launch_cg2<BLOCK_N, PB200_EPI_F16>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_F32: return launch_cg2<BLOCK_N, PB200_EPI_F32>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_GELU_F16: return launch_cg2<BLOCK_N, PB200_EPI_GELU_F16>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_RESID_F32: return launch_cg2<BLOCK_N, PB200_EPI_RESID_F32>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_UNPATCH_F32: return launch_cg2<BLOCK_N, PB200_EPI_UNPATCH_F32>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_NCHW_F32: return launch_cg2<BLOCK_N, PB200_EPI_NCHW_F32>(ta, tb, ep, M, N, K, st);
+    }
+    PB_CHECK(false, "gemm: unknown epilogue mode %d", ep.mode);
+    return 1;
+}
+
 // ------------------------------------------------------------------ dispatch
 template <int BLOCK_N, int MODE, int AMODE = 0>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_gemm_epilogue& ep, int M, int N, int K,
@@ -480,16 +683,24 @@ static int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const pb200
     return 1;
 }
 
+static bool gemm_use_cg2(int64_t M) {
+    static const bool off = getenv("PB200_NO_CG2") != nullptr;
+    return !off && M > GEMM_BLOCK_M && sm_count() % 2 == 0;
+}
+
 int gemm_pick_block_n(int64_t M, int64_t N) {
-    // minimise (waves x tile cost); tile cost ~ BLOCK_N plus a fixed per-tile overhead
+    // minimise (waves x tile cost); tile cost ~ BLOCK_N plus a fixed per-tile overhead.  With the 2-SM kernel a work
+    // unit is a 256-row pair tile and there are sm_count/2 pairs.
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const bool cg2 = gemm_use_cg2(M);
     const int cands[3] = {256, 128, 64};
     int best = 128;
     double best_cost = 1e30;
-    const int sms = sm_count() > 0 ? sm_count() : 148;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < (cg2 ? 2 : 3); ++i) {
         const int bn = cands[i];
-        const long tiles = (long)ceil_div(M, GEMM_BLOCK_M) * ceil_div(N, bn);
-        const long waves = (tiles + sms - 1) / sms;
+        const long units = (long)ceil_div(M, cg2 ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M) * ceil_div(N, bn);
+        const long workers = cg2 ? sms / 2 : sms;
+        const long waves = (units + workers - 1) / workers;
         const double cost = (double)waves * (bn + 24);
         if (cost < best_cost) { best_cost = cost; best = bn; }
     }
@@ -510,6 +721,10 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const
         PB_CHECK(ep.rows_per_sample > 0, "gemm: rows_per_sample required");
     static const char* kTags[6] = {"gemm_f16", "gemm_f32", "gemm_gelu_sqsum", "gemm_resid", "gemm_unpatch", "gemm_nchw"};
     ProfScope prof(ep.mode >= 0 && ep.mode < 6 ? kTags[ep.mode] : "gemm", 2.0 * (double)M * (double)N * (double)K, st);
+    if (gemm_use_cg2(M) && block_n >= 128) {
+        if (block_n == 256) return launch_cg2_mode<256>(ta, tb, ep, (int)M, (int)N, (int)K, st);
+        return launch_cg2_mode<128>(ta, tb, ep, (int)M, (int)N, (int)K, st);
+    }
     switch (block_n) {
         case 64: return launch_mode<64>(ta, tb, ep, (int)M, (int)N, (int)K, st);
         case 128: return launch_mode<128>(ta, tb, ep, (int)M, (int)N, (int)K, st);

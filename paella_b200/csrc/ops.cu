@@ -305,15 +305,17 @@ int launch_grn_apply(__half* h, int64_t M, int N, int P, const float* scale, con
 // One-kernel GRN: every CTA recomputes its sample's normaliser mean_n sqrt(sq[b,n]) (N fp32 values from L2), then
 // rescales its rows.  sq_next (the other half of a ping-pong pair) is zeroed for the next block's GEMM epilogue,
 // so the statistic buffer being read is never written in the same launch.
-__global__ void __launch_bounds__(256) grn_fused_kernel(__half* __restrict__ h, int P, int N, const float* __restrict__ sq,
-                                                        float* __restrict__ sq_next, const float* __restrict__ gamma,
+__device__ __forceinline__ float grn_fx(unsigned long long q) { return __ull2float_rn(q) * (1.0f / 16777216.0f); }
+
+__global__ void __launch_bounds__(256) grn_fused_kernel(__half* __restrict__ h, int P, int N, const unsigned long long* __restrict__ sq,
+                                                        unsigned long long* __restrict__ sq_next, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int rows_per_cta, int zero_per_sample) {
     const int b = blockIdx.y;
-    const float* sqb = sq + (int64_t)b * N;
+    const unsigned long long* sqb = sq + (int64_t)b * N;
     float s = 0.f;
-    for (int i = threadIdx.x; i < (N >> 2); i += 256) {
-        const float4 q = *reinterpret_cast<const float4*>(sqb + 4 * i);
-        s += (sqrtf(q.x) + sqrtf(q.y)) + (sqrtf(q.z) + sqrtf(q.w));
+    for (int i = threadIdx.x; i < (N >> 1); i += 256) {
+        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(sqb + 2 * i);
+        s += sqrtf(grn_fx(q.x)) + sqrtf(grn_fx(q.y));
     }
     __shared__ float red[8];
     s = warp_sum(s);
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(256) grn_fused_kernel(__half* __restrict__ h, 
     for (int i = 0; i < 8; ++i) tot += red[i];
     const float inv_denom = 1.0f / (tot / N + 1e-6f);
     if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < zero_per_sample; i += 256) sq_next[(int64_t)b * zero_per_sample + i] = 0.f;
+        for (int i = threadIdx.x; i < zero_per_sample; i += 256) sq_next[(int64_t)b * zero_per_sample + i] = 0ull;
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(P, r0 + rows_per_cta);
     __half* hb = h + ((int64_t)b * P) * N;
@@ -333,10 +335,11 @@ __global__ void __launch_bounds__(256) grn_fused_kernel(__half* __restrict__ h, 
         float sc[8], be[8];
         {
             const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
-            const float4 q0 = *reinterpret_cast<const float4*>(sqb + col), q1 = *reinterpret_cast<const float4*>(sqb + col + 4);
+            const ulonglong2 u0 = *reinterpret_cast<const ulonglong2*>(sqb + col), u1 = *reinterpret_cast<const ulonglong2*>(sqb + col + 2);
+            const ulonglong2 u2 = *reinterpret_cast<const ulonglong2*>(sqb + col + 4), u3 = *reinterpret_cast<const ulonglong2*>(sqb + col + 6);
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
             const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            const float qq[8] = {grn_fx(u0.x), grn_fx(u0.y), grn_fx(u1.x), grn_fx(u1.y), grn_fx(u2.x), grn_fx(u2.y), grn_fx(u3.x), grn_fx(u3.y)};
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(256) grn_fused_kernel(__half* __restrict__ h, 
     }
 }
 
-int launch_grn_fused(__half* h, int B, int P, int N, const float* sq, float* sq_next, int zero_per_sample, const float* gamma,
+int launch_grn_fused(__half* h, int B, int P, int N, const uint64_t* sq, uint64_t* sq_next, int zero_per_sample, const float* gamma,
                      const float* beta, cudaStream_t st) {
     ProfScope prof("grn", (double)B * P * N * 4.0, st);
     PB_CHECK(N % 8 == 0, "grn: N=%d must be a multiple of 8", N);
@@ -374,7 +377,8 @@ int launch_grn_fused(__half* h, int B, int P, int N, const float* sq, float* sq_
     const int rows_per_cta = P >= 16 ? 16 : P;
     dim3 grid(ceil_div(P, rows_per_cta), B);
     PB_CHECK(grid.y <= 65535, "grn: batch too large");
-    grn_fused_kernel<<<grid, 256, 0, st>>>(h, P, N, sq, sq_next, gamma, beta, rows_per_cta, zero_per_sample);
+    grn_fused_kernel<<<grid, 256, 0, st>>>(h, P, N, reinterpret_cast<const unsigned long long*>(sq),
+                                           reinterpret_cast<unsigned long long*>(sq_next), gamma, beta, rows_per_cta, zero_per_sample);
     PB_LAUNCH_CHECK();
     return 0;
 }

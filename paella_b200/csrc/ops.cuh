@@ -29,7 +29,7 @@ int launch_grn_apply(__half* h, int64_t M, int N, int P, const float* scale, con
 
 // both of the above in one launch: h[b,p,n] = h*(1 + gamma[n]*Gx[b,n]/(mean_n Gx + 1e-6)) + beta[n], Gx = sqrt(sq[b,n]);
 // zeroes all B*zero_per_sample floats of sq_next (the other buffer of a ping-pong pair) for the next block
-int launch_grn_fused(__half* h, int B, int P, int N, const float* sq, float* sq_next, int zero_per_sample, const float* gamma,
+int launch_grn_fused(__half* h, int B, int P, int N, const uint64_t* sq, uint64_t* sq_next, int zero_per_sample, const float* gamma,
                      const float* beta, cudaStream_t st);
 
 // gen_r_embedding: r [B] -> [B, c_r]

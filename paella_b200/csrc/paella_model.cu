@@ -320,7 +320,8 @@ struct FeatWs {
     float* xd[PB200_MAX_LEVELS];
     float* xu[PB200_MAX_LEVELS];
     __half *a16, *h16, *qkv16, *o16;
-    float *gsq, *gscale, *r_emb, *film, *y;
+    uint64_t *gsq, *gscale;      // GRN statistic ping/pong (2^-24 fixed point)
+    float *r_emb, *film, *y;
 };
 
 static void plan_features(const pb200_paella* m, int Bt, int H, int W, Arena& ar, FeatWs& ws) {
@@ -338,8 +339,8 @@ static void plan_features(const pb200_paella* m, int Bt, int H, int W, Arena& ar
     ws.h16 = ar.take<__half>(4 * max_mc > m0_emb ? 4 * max_mc : m0_emb);
     ws.qkv16 = ar.take<__half>(3 * max_mc);
     ws.o16 = ar.take<__half>(max_mc);
-    ws.gsq = ar.take<float>((int64_t)Bt * 4 * m->max_c);        // ping
-    ws.gscale = ar.take<float>((int64_t)Bt * 4 * m->max_c);     // pong (second GRN statistic buffer)
+    ws.gsq = ar.take<uint64_t>((int64_t)Bt * 4 * m->max_c);     // ping
+    ws.gscale = ar.take<uint64_t>((int64_t)Bt * 4 * m->max_c);  // pong (second GRN statistic buffer)
     ws.r_emb = ar.take<float>((int64_t)Bt * c.c_r);
     ws.film = ar.take<float>((int64_t)Bt * (m->film_total > 0 ? m->film_total : 4));
     ws.y = ar.take<float>((int64_t)Bt * H * W * c.c_out);
@@ -530,8 +531,8 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
     // timestep embedding and every TimestepBlock's (a, b) at once
     PB_TRY(launch_r_embed(r, Bt, c.c_r, ws.r_emb, st));
     PB_TRY(launch_film_table(ws.r_emb, Bt, c.c_r, m->w<float>(m->film_w), m->w<float>(m->film_b), m->film_total, ws.film, st));
-    PB_CUDA(cudaMemsetAsync(ws.gsq, 0, (size_t)Bt * 4 * m->max_c * sizeof(float), st));
-    float* grn_stat[2] = {ws.gsq, ws.gscale};      // ping-pong: the GRN kernel of block i zeroes the buffer of block i+1
+    PB_CUDA(cudaMemsetAsync(ws.gsq, 0, (size_t)Bt * 4 * m->max_c * sizeof(uint64_t), st));
+    uint64_t* grn_stat[2] = {ws.gsq, ws.gscale};      // ping-pong: the GRN kernel of block i zeroes the buffer of block i+1
     int grn_flip = 0;
 
     // in_mapper + embedding
@@ -578,8 +579,8 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
                     PB_TRY(launch_ln_rows(x, M, ch, 1.0f, 0.0f, ws.a16, nullptr, st));
                 }
                 pb200_gemm_epilogue e1 = epi(PB200_EPI_GELU_F16, m->w<float>(b.b1), ws.h16, 4 * ch);
-                float* stat = grn_stat[grn_flip];
-                float* stat_next = grn_stat[grn_flip ^ 1];
+                uint64_t* stat = grn_stat[grn_flip];
+                uint64_t* stat_next = grn_stat[grn_flip ^ 1];
                 grn_flip ^= 1;
                 e1.sqsum = stat; e1.rows_per_sample = P;
                 PB_TRY(m->gemm(ws.a16, ch, M, ch, b.w1, 4 * (int64_t)ch, e1, st));

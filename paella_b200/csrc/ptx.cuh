@@ -63,6 +63,17 @@ __device__ __forceinline__ void cluster_sync() {     // all threads of all CTAs 
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA's window) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier anywhere in the cluster (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
@@ -81,6 +92,14 @@ __device__ __forceinline__ void tma_load_2d_mcast(const void* tmap, uint32_t bar
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
         " [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+// 2-SM form: data lands in THIS CTA's shared memory, the transaction bytes are credited to `cluster_bar`
+// (the leader CTA's mbarrier, a shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_cg2(const void* tmap, uint32_t cluster_bar, uint32_t smem_dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(cluster_bar), "r"(c0), "r"(c1)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(const void* tmap, uint32_t bar, uint32_t smem_dst, int c0, int c1, int c2,
@@ -129,6 +148,29 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // ... and the arrival is delivered to the barrier at the same offset in every CTA of cta_mask
 __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
+}
+// ---- cta_group::2 (a CTA pair drives one 256-row MMA; issued by the leader CTA only)
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t smem_dst, uint32_t ncols) {   // same warp id in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2_mcast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

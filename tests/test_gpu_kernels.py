@@ -221,11 +221,11 @@ def test_gemm_gelu_sqsum(M, N, K, P):
     bias = torch.randn(N, device=DEV, generator=g) * 0.1
     h = torch.nn.functional.gelu(_ref_mm(a, w) + bias)
     out = torch.zeros(M, N, device=DEV, dtype=torch.float16)
-    sq = torch.zeros(M // P, N, device=DEV)
+    sq = torch.zeros(M // P, N, device=DEV, dtype=torch.int64)       # 2^-24 fixed point, integer atomics
     ops.gemm_f16(a, w, _lib.EPI_GELU_F16, out, bias=bias, sqsum=sq, rows_per_sample=P)
     err = float((out.float() - h).abs().max())
     want_sq = (h * h).view(M // P, P, N).sum(1)
-    rel = float(((sq - want_sq).abs() / (want_sq.abs() + 1e-3)).max())
+    rel = float(((sq.double() / 2 ** 24 - want_sq).abs() / (want_sq.abs() + 1e-3)).max())
     _log("gemm_gelu", {"M": M, "N": N, "K": K, "P": P, "max_abs_err": err, "sq_rel": rel})
     assert err < 1e-2 and rel < 2e-3
 

@@ -215,4 +215,4 @@ def test_default_config_sample_runs_and_is_seed_deterministic(default_model):
     assert int(a.min()) >= 0 and int(a.max()) < 8192
     same = float((a == b).float().mean())
     _log("default_sample_repeat", {"same": same})
-    assert same > 0.98          # bit-identical RNG stream; only float-atomic GRN sums may flip a near-tie
+    assert same > 0.999         # bit-identical RNG stream and order-independent (integer) GRN statistics

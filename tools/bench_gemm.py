@@ -28,7 +28,7 @@ def main():
         bias = torch.randn(N, device=dev)
         if mode == "gelu":
             out = torch.empty(M, N, device=dev, dtype=torch.float16)
-            sq = torch.zeros(M // P, N, device=dev)
+            sq = torch.zeros(M // P, N, device=dev, dtype=torch.int64)
             run = lambda: ops.gemm_f16(a, w, _lib.EPI_GELU_F16, out, bias=bias, sqsum=sq, rows_per_sample=P)
         elif mode == "resid":
             out = torch.randn(M, N, device=dev)
