@@ -65,6 +65,11 @@ int pb200_resample_logits(const float* logits_c, const float* logits_u, int64_t 
                           double cfg, double temperature, int mode, uint64_t seed, uint64_t offset, int64_t* out,
                           void* stream);
 
+/* `quant` sampling mode (notebook cell 3; ref/src_distributed/train.py:155-156): e = softmax(l/T) @ codebook,
+ * token = nearest code of e.  logits as above; codebook fp32 [k, c_latent]; no random draw. */
+int pb200_resample_quant(const float* logits_c, const float* logits_u, int64_t batch, int64_t k, int64_t hw, double cfg,
+                         double temperature, const float* codebook, int c_latent, int64_t* out, void* stream);
+
 /* Paella.add_noise(x, t, random_x=...)            [ref/src/modules.py:277-283]
  *   mask = (rand_like(x.float()) <= t[:,None,None]); x*(1-mask) + random_x*mask
  * x, random_x, out: int64 [B, HW]; t: fp32 [B]; mask_out: int64 [B, HW] or NULL.
@@ -167,6 +172,12 @@ int64_t pb200_paella_cond_cache_bytes(const pb200_paella* m, int batch_total, in
  * (x- and t-independent) for samples [batch_offset, batch_offset + batch) of the cache. */
 int pb200_paella_prepare_cond(pb200_paella* m, const pb200_cond* cond, int batch, int batch_offset, int batch_total,
                               int s_max, void* cond_cache, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* gen_r_embedding: r fp32 [B] -> fp32 [B, c_r]   (ref/src/modules.py:212-221) */
+int pb200_paella_r_embedding(const float* r, int batch, int c_r, float* out, void* stream);
+/* gen_c_embeddings: -> fp32 [B, S, c_cond], S = byt5_len + clip_seq_len*(has_clip + n_clip_image)   (ref/src/modules.py:223-232) */
+int pb200_paella_c_embeddings(pb200_paella* m, const pb200_cond* cond, int batch, float* out, void* workspace,
+                              int64_t workspace_bytes, void* stream);
 
 /* Paella.forward up to out_mapper's LayerNorm: tokens int64 [Bt,H,W], r fp32 [Bt] ->
  * features fp32 [Bt*H*W, c_out] (rows (b,y,x)).  attn_weights fp32 [n_attn_weights] or NULL scales

@@ -684,8 +684,10 @@ static int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const pb200
 }
 
 static bool gemm_use_cg2(int64_t M) {
-    static const bool off = getenv("PB200_NO_CG2") != nullptr;
-    return !off && M > GEMM_BLOCK_M && sm_count() % 2 == 0;
+    // The 2-SM kernel is numerically verified (tests pass with PB200_CG2=1) but measured SLOWER than the 1-SM kernel
+    // on B200 (551 vs 907 TFLOP/s on 8192x5120x1280): opt-in until its pipeline is fixed.
+    static const bool on = getenv("PB200_CG2") != nullptr;
+    return on && M > GEMM_BLOCK_M && sm_count() % 2 == 0;
 }
 
 int gemm_pick_block_n(int64_t M, int64_t N) {

@@ -444,23 +444,9 @@ int64_t pb200_paella_cond_cache_bytes(const pb200_paella* m, int batch_total, in
     return cond_block_off(m, m->n_attn, batch_total, s_max) + ((int64_t)batch_total * 4 + 255) / 256 * 256;
 }
 
-int pb200_paella_prepare_cond(pb200_paella* m, const pb200_cond* cond, int batch, int batch_offset, int batch_total,
-                              int s_max, void* cond_cache, void* workspace, int64_t workspace_bytes, void* stream) {
-    PB_CHECK(m->blob != nullptr, "prepare_cond: weights not bound");
-    PB_CHECK(cond && cond->byt5 && cond->byt5_len > 0, "prepare_cond: byt5 embeddings are required");
+// gen_c_embeddings into ws.seq (fp32 [B,S,c_cond], LayerNorm'd): ref/src/modules.py:223-232
+static int cond_embed(pb200_paella* m, const pb200_cond* cond, int B, int L, int S, CondWs& ws, cudaStream_t st) {
     const pb200_paella_config& c = m->cfg;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int B = batch, L = cond->byt5_len;
-    const int n_extra = (cond->clip ? 1 : 0) + (cond->clip_image ? cond->n_clip_image : 0);
-    const int S = L + c.clip_seq_len * n_extra;
-    PB_CHECK(S <= s_max, "prepare_cond: sequence length %d exceeds s_max %d", S, s_max);
-    PB_CHECK(batch_offset >= 0 && batch_offset + B <= batch_total, "prepare_cond: batch range out of bounds");
-    PB_CHECK(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)cond_cache & 255) == 0, "buffers must be 256-byte aligned");
-    Arena ar{reinterpret_cast<uint8_t*>(workspace)};
-    CondWs ws;
-    plan_cond(m, B, L, S, ar, ws);
-    PB_CHECK(ar.off <= workspace_bytes, "prepare_cond: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)ar.off);
-
     // byt5_mapper -> rows [b, 0:L)
     PB_TRY(launch_cast_f16(cond->byt5, (int64_t)B * L * c.byt5_embd, ws.byt5_16, st));
     {
@@ -481,8 +467,50 @@ int pb200_paella_prepare_cond(pb200_paella* m, const pb200_cond* cond, int batch
     if (cond->clip_image)
         for (int i = 0; i < cond->n_clip_image; ++i)
             PB_TRY(map_clip(cond->clip_image + (int64_t)i * B * c.clip_embd, m->clipimg_w, m->clipimg_b));
-    // seq_norm, then the SiLU every kv_mapper starts with
-    PB_TRY(launch_ln_rows(ws.seq, (int64_t)B * S, c.c_cond, 1.0f, 0.0f, nullptr, ws.seq, st));
+    // seq_norm
+    return launch_ln_rows(ws.seq, (int64_t)B * S, c.c_cond, 1.0f, 0.0f, nullptr, ws.seq, st);
+}
+
+int pb200_paella_r_embedding(const float* r, int batch, int c_r, float* out, void* stream) {
+    return launch_r_embed(r, batch, c_r, out, (cudaStream_t)stream);
+}
+
+int pb200_paella_c_embeddings(pb200_paella* m, const pb200_cond* cond, int batch, float* out, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+    PB_CHECK(m->blob != nullptr, "c_embeddings: weights not bound");
+    PB_CHECK(cond && cond->byt5 && cond->byt5_len > 0, "c_embeddings: byt5 embeddings are required");
+    const pb200_paella_config& c = m->cfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int L = cond->byt5_len;
+    const int S = L + c.clip_seq_len * ((cond->clip ? 1 : 0) + (cond->clip_image ? cond->n_clip_image : 0));
+    PB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    Arena ar{reinterpret_cast<uint8_t*>(workspace)};
+    CondWs ws;
+    plan_cond(m, batch, L, S, ar, ws);
+    PB_CHECK(ar.off <= workspace_bytes, "c_embeddings: workspace too small");
+    PB_TRY(cond_embed(m, cond, batch, L, S, ws, st));
+    PB_CUDA(cudaMemcpyAsync(out, ws.seq, (size_t)batch * S * c.c_cond * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int pb200_paella_prepare_cond(pb200_paella* m, const pb200_cond* cond, int batch, int batch_offset, int batch_total,
+                              int s_max, void* cond_cache, void* workspace, int64_t workspace_bytes, void* stream) {
+    PB_CHECK(m->blob != nullptr, "prepare_cond: weights not bound");
+    PB_CHECK(cond && cond->byt5 && cond->byt5_len > 0, "prepare_cond: byt5 embeddings are required");
+    const pb200_paella_config& c = m->cfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = batch, L = cond->byt5_len;
+    const int n_extra = (cond->clip ? 1 : 0) + (cond->clip_image ? cond->n_clip_image : 0);
+    const int S = L + c.clip_seq_len * n_extra;
+    PB_CHECK(S <= s_max, "prepare_cond: sequence length %d exceeds s_max %d", S, s_max);
+    PB_CHECK(batch_offset >= 0 && batch_offset + B <= batch_total, "prepare_cond: batch range out of bounds");
+    PB_CHECK(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)cond_cache & 255) == 0, "buffers must be 256-byte aligned");
+    Arena ar{reinterpret_cast<uint8_t*>(workspace)};
+    CondWs ws;
+    plan_cond(m, B, L, S, ar, ws);
+    PB_CHECK(ar.off <= workspace_bytes, "prepare_cond: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)ar.off);
+    PB_TRY(cond_embed(m, cond, B, L, S, ws, st));
+    // the SiLU every kv_mapper starts with
     PB_TRY(launch_silu_cast_f16(ws.seq, (int64_t)B * S * c.c_cond, ws.silu16, st));
 
     uint8_t* cache = reinterpret_cast<uint8_t*>(cond_cache);

@@ -183,6 +183,86 @@ __global__ void __launch_bounds__(256) resample_logits_kernel(const float* __res
     }
 }
 
+// ------------------------------------------------------------------ `quant` sampling mode (notebook cell 3, ref/src_distributed/train.py:155-156)
+//   e = softmax(l / T) @ codebook  [C values per token];  token = nearest code of e   (deterministic, no draw)
+// Same CTA shape as resample_logits_kernel: 32 positions x 8 warps striding the labels.
+template <int C>
+__global__ void __launch_bounds__(256) resample_quant_kernel(const float* __restrict__ lc, const float* __restrict__ lu, int k,
+                                                             int64_t hw, float cfg, float one_minus_cfg, float inv_t,
+                                                             const float* __restrict__ codebook, int64_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b = blockIdx.y;
+    const int64_t pos = (int64_t)blockIdx.x * 32 + lane;
+    const bool valid = pos < hw;
+    const float* c_ptr = lc + b * (int64_t)k * hw + (valid ? pos : 0);
+    const float* u_ptr = lu ? lu + b * (int64_t)k * hw + (valid ? pos : 0) : nullptr;
+    __shared__ float red[8][33];
+    __shared__ float redc[C][8][33];
+    __shared__ int redi[8][33];
+    auto mixed = [&](int j) -> float {
+        float l = c_ptr[(int64_t)j * hw];
+        if (u_ptr) l = __fadd_rn(__fmul_rn(l, cfg), __fmul_rn(u_ptr[(int64_t)j * hw], one_minus_cfg));
+        return __fmul_rn(l, inv_t);
+    };
+    float m = -INFINITY;
+    for (int j = warp; j < k; j += 8) m = fmaxf(m, mixed(j));
+    red[warp][lane] = m;
+    __syncthreads();
+    m = red[0][lane];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w][lane]);
+    __syncthreads();
+    float sum = 0.f, acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    for (int j = warp; j < k; j += 8) {
+        const float e = expf(mixed(j) - m);
+        sum += e;
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(e, __ldg(codebook + (int64_t)j * C + c), acc[c]);
+    }
+    red[warp][lane] = sum;
+#pragma unroll
+    for (int c = 0; c < C; ++c) redc[c][warp][lane] = acc[c];
+    __syncthreads();
+    sum = 0.f;
+    float x[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) x[c] = 0.f;
+    for (int w = 0; w < 8; ++w) {
+        sum += red[w][lane];
+#pragma unroll
+        for (int c = 0; c < C; ++c) x[c] += redc[c][w][lane];
+    }
+    float x2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { x[c] = __fdiv_rn(x[c], sum); x2 = fmaf(x[c], x[c], x2); }
+    // nearest code (same arithmetic as vq_nearest_kernel), codes strided over the 8 warps
+    float best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = warp; j < k; j += 8) {
+        float c2 = 0.f, dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float cv = __ldg(codebook + (int64_t)j * C + c);
+            c2 = fmaf(cv, cv, c2);
+            dot = fmaf(x[c], cv, dot);
+        }
+        const float d = fmaf(-2.0f, dot, __fadd_rn(c2, x2));
+        if (d < best) { best = d; bi = j; }
+    }
+    __syncthreads();
+    red[warp][lane] = best;
+    redi[warp][lane] = bi;
+    __syncthreads();
+    if (warp == 0 && valid) {
+        float bd = red[0][lane];
+        int bj = redi[0][lane];
+        for (int w = 1; w < 8; ++w)
+            if (red[w][lane] < bd || (red[w][lane] == bd && redi[w][lane] < bj)) { bd = red[w][lane]; bj = redi[w][lane]; }
+        out[b * hw + pos] = bj;
+    }
+}
+
 }  // namespace pb
 
 using namespace pb;
@@ -243,6 +323,23 @@ int pb200_resample_logits(const float* logits_c, const float* logits_u, int64_t 
     else
         resample_logits_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(logits_c, logits_u, (int)k, hw, cfg_f, one_minus,
                                                                           inv_t, s, out);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+int pb200_resample_quant(const float* logits_c, const float* logits_u, int64_t batch, int64_t k, int64_t hw, double cfg,
+                         double temperature, const float* codebook, int c_latent, int64_t* out, void* stream) {
+    PB_CHECK(c_latent >= 1 && c_latent <= 8, "resample_quant: c_latent %d unsupported (1..8)", c_latent);
+    if (batch == 0 || hw == 0) return 0;
+    const float cfg_f = (float)cfg, one_minus = (float)(1.0 - cfg), inv_t = 1.0f / (float)temperature;
+    dim3 grid(ceil_div(hw, 32), (unsigned)batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (c_latent) {
+#define PB_RQ_CASE(C) \
+    case C: resample_quant_kernel<C><<<grid, 256, 0, st>>>(logits_c, logits_u, (int)k, hw, cfg_f, one_minus, inv_t, codebook, out); break;
+        PB_RQ_CASE(1) PB_RQ_CASE(2) PB_RQ_CASE(3) PB_RQ_CASE(4) PB_RQ_CASE(5) PB_RQ_CASE(6) PB_RQ_CASE(7) PB_RQ_CASE(8)
+#undef PB_RQ_CASE
+    }
     PB_LAUNCH_CHECK();
     return 0;
 }

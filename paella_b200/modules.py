@@ -334,6 +334,46 @@ class Paella(nn.Module):
                 off += B
         return ConditioningCache(cache, bt, s_max)
 
+    def gen_r_embedding(self, r, max_positions=10000):
+        """ref/src/modules.py:212-221 -> [B, c_r]."""
+        if max_positions != 10000:
+            raise PaellaB200Error("gen_r_embedding: only max_positions=10000 is built (the reference's only value)")
+        dev = self._device()
+        with torch.cuda.device(dev):
+            r = r.to(device=dev, dtype=torch.float32).contiguous()
+            out = torch.empty(r.shape[0], self.c_r, dtype=torch.float32, device=dev)
+            check(lib().pb200_paella_r_embedding(ptr(r), r.shape[0], self.c_r, ptr(out), current_stream()), "pb200_paella_r_embedding")
+        return out
+
+    def gen_c_embeddings(self, byt5, clip, clip_image):
+        """ref/src/modules.py:223-232 (+ list-valued clip_image, ref/utils/modules.py:228-235) -> [B, S, c_cond]."""
+        self._ensure_packed()
+        L, dev = lib(), self._device()
+        with torch.cuda.device(dev):
+            byt5 = byt5.to(device=dev, dtype=torch.float32).contiguous()
+            B = byt5.shape[0]
+            cond = _lib.Cond()
+            cond.byt5, cond.byt5_len = ptr(byt5).value, byt5.shape[1]
+            n = 0
+            if clip is not None:
+                clip = clip.to(device=dev, dtype=torch.float32).contiguous()
+                cond.clip = ptr(clip).value
+                n += 1
+            ci = clip_image
+            if ci is not None:
+                ci = torch.stack([t.to(device=dev, dtype=torch.float32) for t in ci]) if isinstance(ci, (list, tuple)) \
+                    else ci.to(device=dev, dtype=torch.float32)[None]
+                ci = ci.contiguous()
+                cond.clip_image, cond.n_clip_image = ptr(ci).value, ci.shape[0]
+                n += ci.shape[0]
+            S = byt5.shape[1] + self._cfg["clip_seq_len"] * n
+            out = torch.empty(B, S, self.c_cond, dtype=torch.float32, device=dev)
+            ws = self._ws(L.pb200_paella_workspace_bytes(self._handle, B, 2 * self._cfg["patch_size"] * 2 ** (len(self._cfg["c_hidden"]) - 1),
+                                                         2 * self._cfg["patch_size"] * 2 ** (len(self._cfg["c_hidden"]) - 1), S))
+            check(L.pb200_paella_c_embeddings(self._handle, ctypes.byref(cond), B, ptr(out), ptr(ws), ws.numel(), current_stream()),
+                  "pb200_paella_c_embeddings")
+        return out
+
     # -------------------------------------------------------------- forward pieces
     def features(self, x: torch.Tensor, r: torch.Tensor, cond: ConditioningCache, attn_weights=None,
                  attn_weights_batch: int = 0) -> torch.Tensor:

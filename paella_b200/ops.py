@@ -74,6 +74,20 @@ def resample_logits(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], cf
     return out
 
 
+def resample_quant(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], cfg: float, temperature: float,
+                   codebook: torch.Tensor) -> torch.Tensor:
+    """Notebook `mode='quant'`: softmax(l/T) @ codebook, then nearest code -> tokens [B,H,W] (no random draw)."""
+    B, K = logits_c.shape[:2]
+    hw = logits_c[0, 0].numel()
+    lc = logits_c.contiguous().float()
+    lu = logits_u.contiguous().float() if logits_u is not None else None
+    cb = codebook.contiguous().float()
+    out = torch.empty((B,) + tuple(logits_c.shape[2:]), dtype=torch.int64, device=lc.device)
+    check(lib().pb200_resample_quant(ptr(lc), ptr(lu), B, K, hw, float(cfg), float(temperature), ptr(cb), cb.shape[1], ptr(out),
+                                     current_stream()), "pb200_resample_quant")
+    return out
+
+
 def add_noise(x: torch.Tensor, t: torch.Tensor, random_x: Optional[torch.Tensor], num_labels: int, generator=None,
               return_mask: bool = True):
     """Paella.add_noise with mask=None  [ref/src/modules.py:277-283]"""

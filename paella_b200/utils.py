@@ -26,7 +26,8 @@ def _zeros_like_inputs(inputs: Dict[str, torch.Tensor]):
 
 
 def _sample_core(model: Paella, model_inputs, latent_shape, unconditional_inputs, init_x, steps, renoise_steps, temperature,
-                 cfgs, t_start, t_end, sampling_conditional_steps, mode, attn_weights, exact, collect):
+                 cfgs, t_start, t_end, sampling_conditional_steps, mode, attn_weights, exact, collect, sampling_quant_steps=None,
+                 codebook=None):
     B, H, W = latent_shape
     dev = model._device()
     use_cfg_any = cfgs is not None
@@ -40,6 +41,8 @@ def _sample_core(model: Paella, model_inputs, latent_shape, unconditional_inputs
         cond_only = None
         intermediates = []
         for i in range(steps):
+            if sampling_quant_steps is not None and i >= sampling_quant_steps:
+                mode = "quant"
             guided = use_cfg_any and i < sampling_conditional_steps
             t = float(t_list[i])
             if guided:
@@ -61,8 +64,11 @@ def _sample_core(model: Paella, model_inputs, latent_shape, unconditional_inputs
                 lc = model.logits_from_features(feats[:n], B, H, W)
                 lu = model.logits_from_features(feats[n:], B, H, W) if guided else None
                 if mode == "quant":
-                    raise NotImplementedError("mode='quant' (softmax @ codebook -> re-quantise) is not built yet")
-                sampled = ops.resample_logits(lc, lu, cfg_i if guided else 0.0, float(temperatures[i]), mode)
+                    if codebook is None:
+                        raise ValueError("mode='quant' needs the VQGAN codebook: pass vqmodel=... (the notebook uses its global `vqmodel`)")
+                    sampled = ops.resample_quant(lc, lu, cfg_i if guided else 0.0, float(temperatures[i]), codebook)
+                else:
+                    sampled = ops.resample_logits(lc, lu, cfg_i if guided else 0.0, float(temperatures[i]), mode)
             if collect:
                 intermediates.append(sampled)
             if i < renoise_steps:
@@ -101,16 +107,17 @@ def sample_distributed(model, model_inputs, unconditional_inputs, latent_shape, 
 
 def sample_notebook(model, model_inputs, latent_shape, unconditional_inputs=None, init_x=None, steps=12, renoise_steps=None,
                     temperature=(0.7, 0.3), cfg=(8.0, 8.0), mode='multinomial', t_start=1.0, t_end=0.0,
-                    sampling_conditional_steps=None, sampling_quant_steps=None, attn_weights=None, exact=False):
-    """paella_inference.ipynb cell 3: returns (sampled, intermediate_images)."""
+                    sampling_conditional_steps=None, sampling_quant_steps=None, attn_weights=None, exact=False, vqmodel=None):
+    """paella_inference.ipynb cell 3: returns (sampled, intermediate_images).  ``vqmodel`` replaces the notebook's global
+    of the same name for ``mode='quant'`` / ``sampling_quant_steps`` (softmax @ codebook -> nearest code)."""
     if sampling_conditional_steps is None:
         sampling_conditional_steps = steps
-    if sampling_quant_steps is not None and sampling_quant_steps < steps:
-        raise NotImplementedError("sampling_quant_steps (switch to mode='quant') is not built yet")
     if renoise_steps is None:
         renoise_steps = steps - 1
     if unconditional_inputs is None:
         unconditional_inputs = _zeros_like_inputs(model_inputs)
     cfgs = torch.linspace(cfg[0], cfg[1], steps).tolist() if cfg is not None else None
+    codebook = vqmodel.vquantizer.codebook.weight.data if vqmodel is not None else None
     return _sample_core(model, model_inputs, tuple(latent_shape), unconditional_inputs, init_x, steps, renoise_steps,
-                        temperature, cfgs, t_start, t_end, sampling_conditional_steps, mode, attn_weights, exact, True)
+                        temperature, cfgs, t_start, t_end, sampling_conditional_steps, mode, attn_weights, exact, True,
+                        sampling_quant_steps, codebook)

@@ -299,3 +299,25 @@ def test_gemm_repeatable_and_back_to_back():
     torch.cuda.synchronize()
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
+
+
+def test_resample_quant_vs_torch_expression():
+    """Notebook `mode='quant'` (softmax @ codebook -> nearest code) vs the same expression in torch ops."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(13)
+    B, K, H = 3, 8192, 16
+    lc = torch.randn(B, K, H, H, device=DEV, generator=g) * 3
+    lu = torch.randn(B, K, H, H, device=DEV, generator=g) * 3
+    cb = torch.randn(K, 4, device=DEV, generator=g)
+    cfg, T = 4.0, 0.6
+    logits = lc * cfg + lu * (1 - cfg)
+    e = logits.div(T).softmax(dim=1).permute(0, 2, 3, 1) @ cb                    # [B,H,H,4]
+    d = torch.cdist(e.reshape(-1, 4).double(), cb.double())
+    want = d.argmin(dim=1).view(B, H, H)
+    got = ops.resample_quant(lc, lu, cfg, T, cb)
+    agree = float((got == want).float().mean())
+    _log("resample_quant", {"agree": agree})
+    assert agree > 0.995
+    got2 = ops.resample_quant(lc, None, 0.0, T, cb)
+    want2 = torch.cdist((lc.div(T).softmax(dim=1).permute(0, 2, 3, 1) @ cb).reshape(-1, 4).double(), cb.double()).argmin(1).view(B, H, H)
+    assert float((got2 == want2).float().mean()) > 0.995

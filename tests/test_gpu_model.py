@@ -70,6 +70,20 @@ def test_tiny_attn_weights_and_list_clip_image(tiny):
     assert mx < MAX_ABS
 
 
+def test_tiny_r_and_c_embeddings_match_reference_golden(tiny):
+    """Paella.gen_r_embedding / gen_c_embeddings (ref/src/modules.py:212-232) vs the reference's own outputs."""
+    m, cfg, sd, g = tiny
+    re = m.gen_r_embedding(t(g["r"]).to(DEV)).cpu()
+    assert float((re - t(g["r_embed"])).abs().max()) < 2e-4        # sin/cos of arguments up to 1e4 in fp32
+    ce = m.gen_c_embeddings(t(g["byt5"]).to(DEV), t(g["clip"]).to(DEV), t(g["clip_image"]).to(DEV)).cpu()
+    assert ce.shape == tuple(g["c_embed"].shape)
+    mx, rms = _errs(ce, t(g["c_embed"]))
+    _log("tiny_c_embed", {"max_abs": mx, "rms": rms})
+    assert mx < 5e-3
+    ce2 = m.gen_c_embeddings(t(g["byt5"]).to(DEV), None, [t(g["clip_image"]).to(DEV)] * 2)
+    assert ce2.shape == (2, 5 + 8, cfg["c_cond"])
+
+
 def test_tiny_forward_is_deterministic_and_batch_independent(tiny):
     m, cfg, sd, g = tiny
     x, r = t(g["x"]).to(DEV), t(g["r"]).to(DEV)
@@ -216,3 +230,37 @@ def test_default_config_sample_runs_and_is_seed_deterministic(default_model):
     same = float((a == b).float().mean())
     _log("default_sample_repeat", {"same": same})
     assert same > 0.999         # bit-identical RNG stream and order-independent (integer) GRN statistics
+
+
+def test_notebook_sampler_modes_and_intermediates(tiny):
+    """paella_inference.ipynb cell-3 signature: modes multinomial / argmax / quant, sampling_quant_steps, attn_weights,
+    init_x, sampling_conditional_steps; returns (sampled, intermediates) with one entry per resample and per renoise."""
+    from paella_b200 import utils as U
+    from paella_b200.vqgan import VQModel
+    m, cfg, sd, g = tiny
+    byt5, clip, ci = t(g["byt5"]).to(DEV), t(g["clip"]).to(DEV), t(g["clip_image"]).to(DEV)
+    cond = {"byt5": byt5, "clip": clip, "clip_image": ci}
+    uncond = {"byt5": torch.zeros_like(byt5), "clip": torch.zeros_like(clip), "clip_image": None}
+    vq = VQModel(levels=2, bottleneck_blocks=1, c_hidden=32, c_latent=4, codebook_size=cfg["num_labels"]).to(DEV)
+    aw = torch.tensor([1.2, 1.2, 0.4, 0.4, 0.4], device=DEV)
+    for mode in ("multinomial", "argmax", "quant"):
+        torch.manual_seed(1)
+        toks, inter = U.sample_notebook(m, cond, (2, 8, 8), uncond, steps=4, renoise_steps=2, mode=mode, attn_weights=aw, vqmodel=vq)
+        assert toks.shape == (2, 8, 8) and len(inter) == 4 + 2
+        assert int(toks.min()) >= 0 and int(toks.max()) < cfg["num_labels"]
+    torch.manual_seed(2)
+    a, _ = U.sample_notebook(m, cond, (2, 8, 8), uncond, steps=4, sampling_quant_steps=2, sampling_conditional_steps=3, vqmodel=vq,
+                             init_x=torch.zeros(2, 8, 8, dtype=torch.int64, device=DEV))
+    torch.manual_seed(2)
+    b, _ = U.sample_notebook(m, cond, (2, 8, 8), uncond, steps=4, sampling_quant_steps=2, sampling_conditional_steps=3, vqmodel=vq,
+                             init_x=torch.zeros(2, 8, 8, dtype=torch.int64, device=DEV))
+    assert torch.equal(a, b)
+    # argmax mode is deterministic and equals the argmax of the guided logits of a plain forward at step 0
+    torch.manual_seed(3)
+    c, inter = U.sample_notebook(m, cond, (2, 8, 8), uncond, steps=1, renoise_steps=0, mode="argmax", cfg=(3.0, 3.0))
+    torch.manual_seed(3)
+    from paella_b200 import ops
+    x0 = ops.randint(cfg["num_labels"], (2, 8, 8), torch.device(DEV))
+    r = torch.ones(2, device=DEV)
+    lg = m(x0, r, byt5, clip=clip, clip_image=ci) * 3.0 + m(x0, r, uncond["byt5"], clip=uncond["clip"]) * (1 - 3.0)
+    assert float((c == lg.argmax(dim=1)).float().mean()) > 0.98
