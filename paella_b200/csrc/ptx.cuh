@@ -71,7 +71,10 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
 }
 // arrive on an mbarrier anywhere in the cluster (address from mapa)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+    // default (.release.cta) semantics as in CUTLASS' ClusterBarrier::arrive(cta_id): with an explicit
+    // .release.cluster ptxas emits MEMBAR.ALL.GPU per arrive, which throttled the peer CTA's TMA producer to one
+    // stage per ~1800 cycles (ncu source view, profiles/r01_cg2_gemm_notes.md)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 
 // ------------------------------------------------------------------ TMA
