@@ -694,11 +694,16 @@ static bool gemm_use_cg2(int64_t M) {
     return !off && M > GEMM_BLOCK_M && sm_count() % 2 == 0;
 }
 
-int gemm_pick_block_n(int64_t M, int64_t N) {
-    // minimise (waves x tile cost); tile cost ~ BLOCK_N plus a fixed per-tile overhead.  With the 2-SM kernel a work
-    // unit is a 256-row pair tile and there are sm_count/2 pairs.
+int gemm_pick_block_n(int64_t M, int64_t N, int64_t K, bool allow_cg2) {
+    // Cycle model per candidate BLOCK_N (measured anchors on B200, profiles/r01_cg2_gemm_notes.md):
+    //   tensor   : waves x k-blocks x 4 MMAs x (BLOCK_N/2 cycles per 128-row MMA)
+    //   L2->SM   : all tiles' operand bytes / ~6300 B/clk (the fabric saturates at ~13 TB/s): per k-block a CTA pulls
+    //              its 128x64 A tile and BLOCK_N x 64 of W (1-SM kernel) or half of that W (2-SM kernel)
+    //   per tile : ~2500 cycles of fill/drain + epilogue tail
+    // and pick the minimum.  The 2-SM kernel's work unit is a 256-row pair tile on sm_count/2 pairs.
     const int sms = sm_count() > 0 ? sm_count() : 148;
-    const bool cg2 = gemm_use_cg2(M);
+    const bool cg2 = allow_cg2 && gemm_use_cg2(M);
+    const long n_kb = K > 0 ? (long)ceil_div(K, GEMM_BLOCK_K) : 16;
     const int cands[3] = {256, 128, 64};
     int best = 128;
     double best_cost = 1e30;
@@ -707,7 +712,10 @@ int gemm_pick_block_n(int64_t M, int64_t N) {
         const long units = (long)ceil_div(M, cg2 ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M) * ceil_div(N, bn);
         const long workers = cg2 ? sms / 2 : sms;
         const long waves = (units + workers - 1) / workers;
-        const double cost = (double)waves * (bn + 24);
+        const double mma = (double)waves * n_kb * 4.0 * (bn / 2.0);
+        const double bytes_per_kb = (cg2 ? 2.0 : 1.0) * 16384.0 + bn * 128.0;
+        const double l2 = (double)units * n_kb * bytes_per_kb / 6300.0;
+        const double cost = (mma > l2 ? mma : l2) + waves * 2500.0;
         if (cost < best_cost) { best_cost = cost; best = bn; }
     }
     return best;
@@ -743,7 +751,7 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const
 int gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int64_t N, int64_t K,
              const pb200_gemm_epilogue& ep, cudaStream_t st) {
     PB_CHECK(K % 8 == 0, "gemm: K=%lld must be a multiple of 8", (long long)K);
-    const int bn = gemm_pick_block_n(M, N);
+    const int bn = gemm_pick_block_n(M, N, K);
     CUtensorMap ta, tb;
     PB_TRY(make_tmap_f16_2d(&ta, a, M, K, lda, GEMM_BLOCK_M));
     PB_TRY(make_tmap_f16_2d(&tb, w, N, K, ldw, bn / 2));      // W box = half a tile (see the producer)

@@ -46,7 +46,9 @@ struct ConvGeom {
 int gemm_conv_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const pb200_gemm_epilogue& ep,
                      const ConvGeom& geom, int64_t N, int64_t K, cudaStream_t st);
 
-int gemm_pick_block_n(int64_t M, int64_t N);
+// BLOCK_N that minimises a tensor / L2-fabric cycle model of the launch (see gemm.cu); allow_cg2=false for the
+// conv (TMA-gather) variants, which run on the 1-SM kernel
+int gemm_pick_block_n(int64_t M, int64_t N, int64_t K = 0, bool allow_cg2 = true);
 
 int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const pb200_gemm_epilogue& ep, int64_t M,
                 int64_t N, int64_t K, cudaStream_t st);

@@ -143,7 +143,7 @@ struct pb200_paella {
     // C = A[M,K] . W[N,K]^T with W at blob offset w_off
     int gemm(const __half* A, int64_t lda, int64_t M, int64_t K, int64_t w_off, int64_t N, const pb200_gemm_epilogue& ep,
              cudaStream_t st) {
-        const int bn = gemm_pick_block_n(M, N);
+        const int bn = gemm_pick_block_n(M, N, K);
         const CUtensorMap *ta, *tb;
         PB_TRY(tmap(A, M, K, lda, GEMM_BLOCK_M, &ta));
         PB_TRY(tmap(w<__half>(w_off), N, K, K, bn / 2, &tb));     // W box = half a tile

@@ -269,7 +269,7 @@ struct pb200_vqgan {
     }
     int gemm(const __half* A, int64_t lda, int64_t M, int64_t K, int64_t w_off, int64_t N, const pb200_gemm_epilogue& ep,
              cudaStream_t st) {
-        const int bn = gemm_pick_block_n(M, N);
+        const int bn = gemm_pick_block_n(M, N, K);
         const CUtensorMap *ta, *tb;
         PB_TRY(tmap2d(A, M, K, lda, GEMM_BLOCK_M, &ta));
         PB_TRY(tmap2d(w<__half>(w_off), N, K, K, bn / 2, &tb));     // W box = half a tile
@@ -448,7 +448,7 @@ int pb200_vqgan_encode(pb200_vqgan* m, const float* img, int batch, int img_h, i
         g.tiles_x = ceil_div(w1, g.tw); g.tiles_y = ceil_div(h1, g.th);
         g.oh = h1; g.ow = w1; g.sy = 1; g.sx = 1; g.py = 0; g.px = 0;
         const int64_t N = c1, K = 16 * (int64_t)m->cpad0;
-        const int bn = gemm_pick_block_n((int64_t)B * g.tiles_x * g.tiles_y * 128, N);
+        const int bn = gemm_pick_block_n((int64_t)B * g.tiles_x * g.tiles_y * 128, N, K, false);
         CUtensorMap ta;
         const int64_t dims[5] = {2 * (int64_t)c0, w0 / 2, 2, h0 / 2, B};
         const int64_t strides[4] = {2 * (int64_t)c0 * 2, (int64_t)w0 * c0 * 2, 2 * (int64_t)w0 * c0 * 2, (int64_t)h0 * w0 * c0 * 2};
@@ -512,7 +512,7 @@ int pb200_vqgan_decode(pb200_vqgan* m, const int64_t* indices, const float* late
         g.tiles_x = ceil_div(w1, g.tw); g.tiles_y = ceil_div(h1, g.th);
         g.oh = h0; g.ow = w0; g.sy = 2; g.sx = 2;
         const int64_t N = c0, K = 4 * (int64_t)m->cpad1;
-        const int bn = gemm_pick_block_n((int64_t)B * g.tiles_x * g.tiles_y * 128, N);
+        const int bn = gemm_pick_block_n((int64_t)B * g.tiles_x * g.tiles_y * 128, N, K, false);
         CUtensorMap ta;
         const int64_t dims[4] = {c1, w1, h1, B};
         const int64_t strides[3] = {(int64_t)c1 * 2, (int64_t)w1 * c1 * 2, (int64_t)h1 * w1 * c1 * 2};
