@@ -84,9 +84,92 @@ int make_tmap_f16_nd(CUtensorMap* tm, const void* ptr, int rank, const int64_t* 
 }
 
 // ------------------------------------------------------------------ epilogue
+// Global operands of a 32-column chunk that do not depend on the accumulator (the fp32 residual row segment).  They
+// are fetched BEFORE the wait on the accumulator: out may alias resid (the model updates x in place), so inside the
+// store loop the compiler must order every load after the previous store -- 8 dependent L2 round trips per chunk,
+// which made the K=1280 out-projection epilogue-bound (73 us for 27 GFLOP).  Preloaded, the latency hides behind
+// the tile's main loop.
+template <int MODE>
+struct EpiPre {};
+template <>
+struct EpiPre<PB200_EPI_RESID_F32> { float4 r[8]; };
+
+// Coalescing.  tcgen05.ld hands every lane one ROW of the chunk (32 consecutive columns), so a direct 16-byte store
+// per lane touches 32 different 128-byte lines per instruction and the LSU serialises them (measured: the fp32
+// epilogue of the 8192x1280x1280 out-projection took 2x its main loop).  The chunk is therefore transposed inside the
+// warp with xor-butterfly shuffles first:
+//   fp32: 8x8 transpose of float4 items in 8-lane groups -> lane (a,b) item i = row 8a+i, columns 4b..4b+3
+//         (a store instruction then writes 4 full 128-byte lines);
+//   fp16: 4x4 transpose of 8-half items in 4-lane groups -> lane (a,b) item i = row 4a+i, columns 8b..8b+7
+//         (8 rows x 64 contiguous bytes per instruction).
+__device__ __forceinline__ void transpose8x8_f4(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 4; s > 0; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int g0 = 0; g0 < 8; ++g0) {
+            if (g0 & s) continue;
+            const int g1 = g0 | s;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float send = up ? v[g0 * 4 + e] : v[g1 * 4 + e];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+                if (up) v[g0 * 4 + e] = recv;
+                else v[g1 * 4 + e] = recv;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void transpose4x4_u4(uint32_t (&pk)[16], int lane) {
+#pragma unroll
+    for (int s = 2; s > 0; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int g0 = 0; g0 < 4; ++g0) {
+            if (g0 & s) continue;
+            const int g1 = g0 | s;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t send = up ? pk[g0 * 4 + e] : pk[g1 * 4 + e];
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, s);
+                if (up) pk[g0 * 4 + e] = recv;
+                else pk[g1 * 4 + e] = recv;
+            }
+        }
+    }
+}
+// fp16 row-per-lane chunk -> transposed, coalesced store.  `orow` is this lane's output row (or -1 if masked).
+__device__ __forceinline__ void store_chunk_f16(const float (&v)[32], __half* out, int64_t ldo, int64_t orow, int col0,
+                                                int N, int lane) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+    transpose4x4_u4(pk, lane);
+    const int col = col0 + (lane & 3) * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = __shfl_sync(0xffffffffu, orow, (lane & 28) + i);
+        if (r >= 0 && col < N)
+            *reinterpret_cast<uint4*>(out + r * ldo + col) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_preload(const pb200_gemm_epilogue& ep, int M, int N, int row, int col0,
+                                                 EpiPre<MODE>& pre, int lane) {
+    if constexpr (MODE == PB200_EPI_RESID_F32) {
+        const int col = col0 + (lane & 7) * 4;       // transposed layout: item i = row of lane (lane & 24) + i
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = __shfl_sync(0xffffffffu, row, (lane & 24) + i);
+            if (r < M && col < N) pre.r[i] = *reinterpret_cast<const float4*>(ep.resid + (int64_t)r * ep.ldr + col);
+        }
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, int M, int N, int row, int col0,
-                                               float (&v)[32], int lane) {
+                                               float (&v)[32], int lane, const EpiPre<MODE>& pre) {
     const bool row_ok = row < M;
     // ---- bias (indexed by GEMM column in every mode)
     {
@@ -101,40 +184,25 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
         }
     }
     if (MODE == PB200_EPI_F16 || MODE == PB200_EPI_F32) {
-        if (!row_ok) return;
-        int64_t orow = row;
-        if (ep.remap_in > 0) orow = (int64_t)(row / ep.remap_in) * ep.remap_out + (row % ep.remap_in);
+        int64_t orow = row_ok ? row : -1;
+        if (row_ok && ep.remap_in > 0) orow = (int64_t)(row / ep.remap_in) * ep.remap_out + (row % ep.remap_in);
         if (MODE == PB200_EPI_F16) {
-            __half* o = reinterpret_cast<__half*>(ep.out) + orow * ep.ldo + col0;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-                if (col0 + g * 8 < N) {
-                    uint4 pk;
-                    pk.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
-                    pk.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
-                    *reinterpret_cast<uint4*>(o + g * 8) = pk;
-                }
+            store_chunk_f16(v, reinterpret_cast<__half*>(ep.out), ep.ldo, orow, col0, N, lane);
         } else {
-            float* o = reinterpret_cast<float*>(ep.out) + orow * ep.ldo + col0;
+            transpose8x8_f4(v, lane);
+            const int col = col0 + (lane & 7) * 4;
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-                if (col0 + g * 4 < N)
-                    *reinterpret_cast<float4*>(o + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            for (int i = 0; i < 8; ++i) {
+                const int64_t r = __shfl_sync(0xffffffffu, orow, (lane & 24) + i);
+                if (r >= 0 && col < N)
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + r * ep.ldo + col) =
+                        make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+            }
         }
     } else if (MODE == PB200_EPI_GELU_F16) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
-        if (row_ok) {
-            __half* o = reinterpret_cast<__half*>(ep.out) + (int64_t)row * ep.ldo + col0;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-                if (col0 + g * 8 < N) {
-                    uint4 pk;
-                    pk.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
-                    pk.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
-                    *reinterpret_cast<uint4*>(o + g * 8) = pk;
-                }
-        }
+        store_chunk_f16(v, reinterpret_cast<__half*>(ep.out), ep.ldo, row_ok ? (int64_t)row : -1, col0, N, lane);
         if (ep.sqsum) {   // GlobalResponseNorm statistic: sum over the sample's positions of h^2, per channel.
             // Accumulated in 2^-24 fixed point with 64-bit integer atomics: integer addition is associative, so the
             // result does not depend on the order in which warps/CTAs arrive (float atomics made two runs of the same
@@ -176,25 +244,27 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
             }
         }
     } else if (MODE == PB200_EPI_RESID_F32) {
-        if (!row_ok) return;
-        const float* r = ep.resid + (int64_t)row * ep.ldr + col0;
-        float* o = reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col0;
-        const float* fa = nullptr;
-        if (ep.film) fa = ep.film + (int64_t)(row / ep.rows_per_sample) * ep.film_ld + ep.film_off + col0;
+        // (bias was added above in the row-per-lane layout); the rest runs in the transposed, coalesced layout
+        transpose8x8_f4(v, lane);
+        const int col = col0 + (lane & 7) * 4;
+        float* obase = reinterpret_cast<float*>(ep.out);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            if (col0 + g * 4 < N) {
-                const float4 rr = *reinterpret_cast<const float4*>(r + g * 4);
+        for (int i = 0; i < 8; ++i) {
+            const int r = __shfl_sync(0xffffffffu, row, (lane & 24) + i);
+            if (r < M && col < N) {
+                float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (MODE == PB200_EPI_RESID_F32) rr = pre.r[i];
                 float4 y;
-                y.x = fmaf(v[g * 4 + 0], ep.alpha, rr.x); y.y = fmaf(v[g * 4 + 1], ep.alpha, rr.y);
-                y.z = fmaf(v[g * 4 + 2], ep.alpha, rr.z); y.w = fmaf(v[g * 4 + 3], ep.alpha, rr.w);
-                if (fa) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(fa + g * 4));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(fa + N + g * 4));
+                y.x = fmaf(v[i * 4 + 0], ep.alpha, rr.x); y.y = fmaf(v[i * 4 + 1], ep.alpha, rr.y);
+                y.z = fmaf(v[i * 4 + 2], ep.alpha, rr.z); y.w = fmaf(v[i * 4 + 3], ep.alpha, rr.w);
+                if (ep.film) {
+                    const float* fa = ep.film + (int64_t)(r / ep.rows_per_sample) * ep.film_ld + ep.film_off + col;
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(fa));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(fa + N));
                     y.x = fmaf(y.x, 1.0f + a.x, b.x); y.y = fmaf(y.y, 1.0f + a.y, b.y);
                     y.z = fmaf(y.z, 1.0f + a.z, b.z); y.w = fmaf(y.w, 1.0f + a.w, b.w);
                 }
-                *reinterpret_cast<float4*>(o + g * 4) = y;
+                *reinterpret_cast<float4*>(obase + (int64_t)r * ep.ldo + col) = y;
             }
         }
     } else if (MODE == PB200_EPI_UNPATCH_F32) {
@@ -376,8 +446,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const int mt = (unit / n_tiles_n) * (int)csize + (int)crank;
             const int m_idx = mt * GEMM_BLOCK_M;
             const int n_idx = (unit % n_tiles_n) * BLOCK_N;
-            ptx::mbar_wait(tfull_bar(as), aphase);
-            ptx::tc_fence_after();
             int row = m_idx + q * 32 + lane;
             if (AMODE != 0) {   // tile row r = (ly, lx) of a th x tw patch -> output pixel row of the NHWC result
                 const int cb = mt / (geom.tiles_y * geom.tiles_x);
@@ -389,12 +457,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                           ? ((cb * geom.oh + gy * geom.sy + geom.py) * geom.ow + gx * geom.sx + geom.px)
                           : M;      // M = B*oh*ow: out of range -> masked
             }
+            EpiPre<MODE> pre;
+            if (n_idx + half * COLS_PER_WARP < N) epilogue_preload<MODE>(ep, M, N, row, n_idx + half * COLS_PER_WARP, pre, lane);
+            ptx::mbar_wait(tfull_bar(as), aphase);
+            ptx::tc_fence_after();
 #pragma unroll 1
             for (int c = half * COLS_PER_WARP; c < (half + 1) * COLS_PER_WARP; c += 32) {
                 if (n_idx + c >= N) break;
+                if (c != half * COLS_PER_WARP) epilogue_preload<MODE>(ep, M, N, row, n_idx + c, pre, lane);
                 float v[32];
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c), v);
-                epilogue_chunk<MODE>(ep, M, N, row, n_idx + c, v, lane);
+                epilogue_chunk<MODE>(ep, M, N, row, n_idx + c, v, lane, pre);
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -538,15 +611,18 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const uint32_t aphase = (iter >> 1) & 1;
             const int m_idx = (unit / n_tiles_n) * (2 * GEMM_BLOCK_M) + (int)crank * GEMM_BLOCK_M;
             const int n_idx = (unit % n_tiles_n) * BLOCK_N;
+            const int row = m_idx + q * 32 + lane;
+            EpiPre<MODE> pre;
+            if (n_idx + slice * COLS_PER_WARP < N) epilogue_preload<MODE>(ep, M, N, row, n_idx + slice * COLS_PER_WARP, pre, lane);
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
-            const int row = m_idx + q * 32 + lane;
 #pragma unroll 1
             for (int c = slice * COLS_PER_WARP; c < (slice + 1) * COLS_PER_WARP; c += 32) {
                 if (n_idx + c >= N) break;
+                if (c != slice * COLS_PER_WARP) epilogue_preload<MODE>(ep, M, N, row, n_idx + c, pre, lane);
                 float v[32];
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c), v);
-                epilogue_chunk<MODE>(ep, M, N, row, n_idx + c, v, lane);
+                epilogue_chunk<MODE>(ep, M, N, row, n_idx + c, v, lane, pre);
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -701,6 +777,8 @@ int gemm_pick_block_n(int64_t M, int64_t N, int64_t K, bool allow_cg2) {
     //              its 128x64 A tile and BLOCK_N x 64 of W (1-SM kernel) or half of that W (2-SM kernel)
     //   per tile : ~2500 cycles of fill/drain + epilogue tail
     // and pick the minimum.  The 2-SM kernel's work unit is a 256-row pair tile on sm_count/2 pairs.
+    static const int force = getenv("PB200_FORCE_BN") ? atoi(getenv("PB200_FORCE_BN")) : 0;   // experiments only
+    if (force == 64 || force == 128 || force == 256) return force;
     const int sms = sm_count() > 0 ? sm_count() : 148;
     const bool cg2 = allow_cg2 && gemm_use_cg2(M);
     const long n_kb = K > 0 ? (long)ceil_div(K, GEMM_BLOCK_K) : 16;

@@ -220,6 +220,181 @@ __global__ void __launch_bounds__(128) dwconv_ln_kernel(const float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------ depthwise 3x3 conv + LayerNorm (thread per 4 channels)
+// The warp-per-position kernel above issues 9 activation + 9 weight loads per position and float4 chunk and is bound
+// by LSU/L1 issue (measured 40 us at 8192 x 1280, HBM ideal 10 us).  Here a thread owns 4 output channels of a
+// 2-row x 8-column patch of positions: it walks the patch's 4 x 10 input halo once (2.5 loads per output instead of
+// 18), keeps the 16 accumulators in registers, and the CTA (c/4 threads) then reduces the LayerNorm statistics of
+// its 16 positions through shared memory.  Tap order per output is (ky, kx) ascending, as in the kernel above.
+constexpr int DW_PH = 2, DW_PW = 8, DW_NPOS = DW_PH * DW_PW;
+
+__device__ __forceinline__ void fma4(float4& a, const float4& v, const float4& w) {
+    a.x = fmaf(v.x, w.x, a.x); a.y = fmaf(v.y, w.y, a.y); a.z = fmaf(v.z, w.z, a.z); a.w = fmaf(v.w, w.w, a.w);
+}
+
+// sum of s[p] over the CTA's threads for p < 16; result in tot[p] (shared; two __syncthreads)
+__device__ __forceinline__ void block_sum16(float (&s)[DW_NPOS], float* red, float* tot, int n_warps) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // transpose-reduce: after the o = 8,4,2,1 steps lane l holds position (l & 15) summed over its 16-lane half
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const bool up = (lane & o) != 0;
+            const float send = up ? s[i] : s[i + o];
+            const float keep = up ? s[i + o] : s[i];
+            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 16);
+    // lane l < 16 now holds position bitrev-free index: bit o of the lane selected the upper half at step o -> p = l & 15
+    if (lane < DW_NPOS) red[wid * DW_NPOS + lane] = s[0];
+    __syncthreads();
+    if (threadIdx.x < DW_NPOS) {
+        float t = 0.f;
+        for (int i = 0; i < n_warps; ++i) t += red[i * DW_NPOS + threadIdx.x];
+        tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
+template <bool SKIP, int MAXT>
+__global__ void __launch_bounds__(MAXT, (MAXT == 320 ? 2 : 1)) dwconv3_ln_patch_kernel(const float* __restrict__ x, const float* __restrict__ skip,
+                                                                const float* __restrict__ wp, const float* __restrict__ bias,
+                                                                int B, int h, int w, int c, __half* __restrict__ out) {
+    __shared__ float red[32 * DW_NPOS];
+    __shared__ float tot[2][DW_NPOS];
+    const int q = threadIdx.x, nvq = c >> 2;
+    const bool active = q < nvq;
+    const int qc = active ? q : 0;                       // idle threads shadow chunk 0 and never store
+    const int tiles_x = (w + DW_PW - 1) / DW_PW, tiles_y = (h + DW_PH - 1) / DW_PH;
+    const int b = blockIdx.x / (tiles_x * tiles_y);
+    const int tr = blockIdx.x - b * (tiles_x * tiles_y);
+    const int y0 = (tr / tiles_x) * DW_PH, x0 = (tr % tiles_x) * DW_PW;
+
+    float4 acc[DW_PH][DW_PW];
+    {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + qc);
+#pragma unroll
+        for (int oy = 0; oy < DW_PH; ++oy)
+#pragma unroll
+            for (int ox = 0; ox < DW_PW; ++ox) acc[oy][ox] = bv;
+    }
+#pragma unroll
+    for (int r = 0; r < DW_PH + 2; ++r) {
+        const int iy = y0 - 1 + r;
+        if (iy < 0 || iy >= h) continue;                 // CTA-uniform: a zero-padding row contributes nothing
+        // input row r feeds output row oy with ky = r - oy
+        float4 wt[DW_PH][3][SKIP ? 2 : 1];
+#pragma unroll
+        for (int oy = 0; oy < DW_PH; ++oy) {
+            const int ky = r - oy;
+            if (ky < 0 || ky > 2) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int tap = ky * 3 + kx;
+                if (SKIP) {
+                    wt[oy][kx][0] = __ldg(reinterpret_cast<const float4*>(wp + ((int64_t)tap * 2 + 0) * c) + qc);
+                    wt[oy][kx][SKIP ? 1 : 0] = __ldg(reinterpret_cast<const float4*>(wp + ((int64_t)tap * 2 + 1) * c) + qc);
+                } else {
+                    wt[oy][kx][0] = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)tap * c) + qc);
+                }
+            }
+        }
+        const int64_t rowbase = ((int64_t)b * h + iy) * w;
+#pragma unroll
+        for (int j = 0; j < DW_PW + 2; ++j) {
+            const int ix = x0 - 1 + j;
+            const bool ok = ix >= 0 && ix < w;
+            const int64_t ipos = rowbase + (ok ? ix : x0);
+            float4 v0, v1;
+            if (SKIP) {
+                // output channels 4q..4q+3 read concatenated [x, skip] channels 8q..8q+7
+                const int cc = 8 * qc;
+                const float* src = cc < c ? x + ipos * c + cc : skip + ipos * c + (cc - c);
+                v0 = *reinterpret_cast<const float4*>(src);
+                v1 = *reinterpret_cast<const float4*>(src + 4);
+            } else {
+                v0 = *(reinterpret_cast<const float4*>(x + ipos * c) + qc);
+                v1 = v0;
+            }
+            if (!ok) { v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0; }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ox = j - kx;
+                if (ox < 0 || ox >= DW_PW) continue;
+#pragma unroll
+                for (int oy = 0; oy < DW_PH; ++oy) {
+                    const int ky = r - oy;
+                    if (ky < 0 || ky > 2) continue;
+                    float4& a = acc[oy][ox];
+                    if (SKIP) {
+                        const float4 wa = wt[oy][kx][0], wb = wt[oy][kx][SKIP ? 1 : 0];
+                        a.x = fmaf(v0.x, wa.x, fmaf(v0.y, wb.x, a.x));
+                        a.y = fmaf(v0.z, wa.y, fmaf(v0.w, wb.y, a.y));
+                        a.z = fmaf(v1.x, wa.z, fmaf(v1.y, wb.z, a.z));
+                        a.w = fmaf(v1.z, wa.w, fmaf(v1.w, wb.w, a.w));
+                    } else {
+                        fma4(a, v0, wt[oy][kx][0]);
+                    }
+                }
+            }
+        }
+    }
+    // ---- LayerNorm over channels for the 16 positions (two-pass, like F.layer_norm)
+    const int n_warps = blockDim.x >> 5;
+    float s[DW_NPOS];
+#pragma unroll
+    for (int p = 0; p < DW_NPOS; ++p) {
+        const float4 a = acc[p / DW_PW][p % DW_PW];
+        s[p] = active ? (a.x + a.y) + (a.z + a.w) : 0.f;
+    }
+    block_sum16(s, red, tot[0], n_warps);
+    const float inv_c = 1.0f / c;
+#pragma unroll
+    for (int p = 0; p < DW_NPOS; ++p) {
+        const float mean = tot[0][p] * inv_c;
+        const float4 a = acc[p / DW_PW][p % DW_PW];
+        const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+        s[p] = active ? (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) : 0.f;
+    }
+    block_sum16(s, red, tot[1], n_warps);
+    if (!active) return;
+#pragma unroll
+    for (int p = 0; p < DW_NPOS; ++p) {
+        const int y = y0 + p / DW_PW, xx = x0 + p % DW_PW;
+        if (y >= h || xx >= w) continue;
+        const float mean = tot[0][p] * inv_c;
+        const float rstd = ln_rstd(tot[1][p] * inv_c);
+        const float4 a = acc[p / DW_PW][p % DW_PW];
+        uint2 pk;
+        pk.x = pack_half2((a.x - mean) * rstd, (a.y - mean) * rstd);
+        pk.y = pack_half2((a.z - mean) * rstd, (a.w - mean) * rstd);
+        *reinterpret_cast<uint2*>(out + (((int64_t)b * h + y) * w + xx) * c + q * 4) = pk;
+    }
+}
+
+static int dwconv3_patch_launch(const float* x, const float* skip, const float* wp, const float* bias, int B, int h, int w,
+                                int c, __half* out, cudaStream_t st) {
+    const int64_t grid = (int64_t)B * ceil_div(h, DW_PH) * ceil_div(w, DW_PW);
+    PB_CHECK(grid < (1ll << 31), "dwconv: grid too large");
+    const int threads = ceil_div(c / 4, 32) * 32;
+#define PB_DW_LAUNCH(MAXT)                                                                                              \
+    do {                                                                                                                \
+        if (skip)                                                                                                       \
+            dwconv3_ln_patch_kernel<true, MAXT><<<(unsigned)grid, threads, 0, st>>>(x, skip, wp, bias, B, h, w, c, out); \
+        else                                                                                                            \
+            dwconv3_ln_patch_kernel<false, MAXT><<<(unsigned)grid, threads, 0, st>>>(x, skip, wp, bias, B, h, w, c, out); \
+    } while (0)
+    if (threads <= 64) PB_DW_LAUNCH(64);
+    else if (threads <= 160) PB_DW_LAUNCH(160);
+    else if (threads <= 320) PB_DW_LAUNCH(320);
+    else PB_DW_LAUNCH(640);
+#undef PB_DW_LAUNCH
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int NV>
 static int dwconv_dispatch(const float* x, const float* skip, const float* wp, const float* bias, int B, int h, int w,
                            int c, int k, __half* out, cudaStream_t st) {
@@ -238,6 +413,8 @@ int launch_dwconv_ln(const float* x, const float* skip, const float* w_packed, c
     ProfScope prof("dwconv_ln", (double)B * h * w * c * (skip ? 10.0 : 6.0), st);
     PB_CHECK(c % 8 == 0, "dwconv: c=%d must be a multiple of 8", c);
     PB_CHECK(k % 2 == 1, "dwconv: kernel_size %d must be odd", k);
+    static const bool old_kernel = getenv("PB200_DWCONV_WARP") != nullptr;      // A/B knob
+    if (k == 3 && c <= 2560 && !old_kernel) return dwconv3_patch_launch(x, skip, w_packed, bias, B, h, w, c, out, st);
     if (c <= 128) return dwconv_dispatch<1>(x, skip, w_packed, bias, B, h, w, c, k, out, st);
     if (c <= 640) return dwconv_dispatch<5>(x, skip, w_packed, bias, B, h, w, c, k, out, st);
     if (c <= 1280) return dwconv_dispatch<10>(x, skip, w_packed, bias, B, h, w, c, k, out, st);
@@ -307,30 +484,29 @@ int launch_grn_apply(__half* h, int64_t M, int N, int P, const float* scale, con
 // so the statistic buffer being read is never written in the same launch.
 __device__ __forceinline__ float grn_fx(unsigned long long q) { return __ull2float_rn(q) * (1.0f / 16777216.0f); }
 
-__global__ void __launch_bounds__(256) grn_fused_kernel(__half* __restrict__ h, int P, int N, const unsigned long long* __restrict__ sq,
+__global__ void __launch_bounds__(384) grn_fused_kernel(__half* __restrict__ h, int P, int N, const unsigned long long* __restrict__ sq,
                                                         unsigned long long* __restrict__ sq_next, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int rows_per_cta, int zero_per_sample) {
     const int b = blockIdx.y;
     const unsigned long long* sqb = sq + (int64_t)b * N;
     float s = 0.f;
-    for (int i = threadIdx.x; i < (N >> 1); i += 256) {
+    for (int i = threadIdx.x; i < (N >> 1); i += blockDim.x) {
         const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(sqb + 2 * i);
         s += sqrtf(grn_fx(q.x)) + sqrtf(grn_fx(q.y));
     }
-    __shared__ float red[8];
+    __shared__ float red[12];
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
     float tot = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) tot += red[i];
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
     const float inv_denom = 1.0f / (tot / N + 1e-6f);
     if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < zero_per_sample; i += 256) sq_next[(int64_t)b * zero_per_sample + i] = 0ull;
+        for (int i = threadIdx.x; i < zero_per_sample; i += blockDim.x) sq_next[(int64_t)b * zero_per_sample + i] = 0ull;
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(P, r0 + rows_per_cta);
     __half* hb = h + ((int64_t)b * P) * N;
-    for (int ch = threadIdx.x; ch < (N >> 3); ch += 256) {
+    for (int ch = threadIdx.x; ch < (N >> 3); ch += blockDim.x) {
         const int col = ch * 8;
         float sc[8], be[8];
         {
@@ -373,11 +549,16 @@ int launch_grn_fused(__half* h, int B, int P, int N, const uint64_t* sq, uint64_
     ProfScope prof("grn", (double)B * P * N * 4.0, st);
     PB_CHECK(N % 8 == 0, "grn: N=%d must be a multiple of 8", N);
     if (B == 0 || P == 0) return 0;
-    // ~16 rows per CTA keeps the normaliser recomputation (N sqrt) small next to the rescale (rows * N)
-    const int rows_per_cta = P >= 16 ? 16 : P;
+    // ~16 rows per CTA keeps the normaliser recomputation (N sqrt) small next to the rescale (rows * N); 8 when
+    // that would leave SMs idle.  The block size divides the N/8 column chunks evenly (N=5120 -> 2 per thread of 320,
+    // N=2560 -> 1): with a fixed 256 the last pass ran 25-50% full.
+    int rows_per_cta = P >= 16 ? 16 : P;
+    if ((int64_t)ceil_div(P, rows_per_cta) * B < 2 * sm_count() && rows_per_cta > 8) rows_per_cta = 8;
     dim3 grid(ceil_div(P, rows_per_cta), B);
     PB_CHECK(grid.y <= 65535, "grn: batch too large");
-    grn_fused_kernel<<<grid, 256, 0, st>>>(h, P, N, reinterpret_cast<const unsigned long long*>(sq),
+    const int nch = N >> 3;
+    const int threads = ceil_div(ceil_div(nch, ceil_div(nch, 384)), 32) * 32;
+    grn_fused_kernel<<<grid, threads, 0, st>>>(h, P, N, reinterpret_cast<const unsigned long long*>(sq),
                                            reinterpret_cast<unsigned long long*>(sq_next), gamma, beta, rows_per_cta, zero_per_sample);
     PB_LAUNCH_CHECK();
     return 0;

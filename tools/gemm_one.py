@@ -24,6 +24,12 @@ elif mode == "resid":
     out = torch.randn(M, N, device=dev)
     film = torch.randn(M // P, 2 * N, device=dev) * 0.1
     run = lambda: ops.gemm_f16(a, w, _lib.EPI_RESID_F32, out, bias=bias, resid=out, rows_per_sample=P, film=film)
+elif mode == "resid_nofilm":
+    out = torch.randn(M, N, device=dev)
+    run = lambda: ops.gemm_f16(a, w, _lib.EPI_RESID_F32, out, bias=bias, resid=out)
+elif mode == "f32":
+    out = torch.empty(M, N, device=dev)
+    run = lambda: ops.gemm_f16(a, w, _lib.EPI_F32, out, bias=bias)
 else:
     out = torch.empty(M, N, device=dev, dtype=torch.float16)
     run = lambda: ops.gemm_f16(a, w, _lib.EPI_F16, out, bias=bias)
