@@ -38,18 +38,23 @@ constexpr int ATT_BM = 64;   // queries per CTA (4 warps x 16)
 constexpr int ATT_BN = 64;   // keys per chunk
 constexpr float NEG_BIG = -1e30f;
 
+// One CTA per (64 queries, head, sample); each warp owns 16 queries and walks the keys in 64-key chunks
+// (double-buffered cp.async).  Tried on B200 and dropped: splitting the KEYS over the warps for the <= 16-query levels
+// (flash-decoding inside the CTA) -- 20.7 vs 19.6 ms per bench step, the extra shared memory costs a resident CTA.
 template <int HD>
 __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     constexpr int LDS = HD + 8;           // padded row: (HD+8)*2 bytes is an odd multiple of 16 -> conflict-free ldmatrix
     constexpr int CPR = HD / 8;           // 16-byte chunks per row
+    constexpr int QROWS = ATT_BM;
+    constexpr int n_buf = 2;
     extern __shared__ __align__(16) __half smem_att[];
-    __half* sQ = smem_att;                                   // [ATT_BM][LDS]
-    __half* sKb = smem_att + ATT_BM * LDS;                    // [2][ATT_BN][LDS]   double-buffered K
-    __half* sVb = sKb + 2 * ATT_BN * LDS;                     // [2][ATT_BN][LDS]   double-buffered V
+    __half* sQ = smem_att;                                   // [QROWS][LDS]
+    __half* sKb = smem_att + QROWS * LDS;                     // [n_buf][ATT_BN][LDS]
+    __half* sVb = sKb + n_buf * ATT_BN * LDS;                 // [n_buf][ATT_BN][LDS]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int q0 = blockIdx.x * ATT_BM, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * QROWS, h = blockIdx.y, b = blockIdx.z;
     const int E = p.E;
     const int64_t ldq = 3 * (int64_t)E, ldc = 2 * (int64_t)E;
     const int n_self = p.self_attn ? p.P : 0;
@@ -80,22 +85,18 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
             cp_async16(smem_u32(sV + r * LDS + cc * 8), vs, nbytes);
         }
     };
+    // Q rides in the same cp.async group as the first K/V chunk (a register-staged Q load cost 5 serialised global
+    // round trips before anything else could start: 22% of the kernel's stall samples in ncu)
+    for (int c = tid; c < QROWS * CPR; c += 128) {
+        const int r = c / CPR, cc = c - r * CPR;
+        const bool ok = q0 + r < p.P;
+        cp_async16(smem_u32(sQ + r * LDS + cc * 8), ok ? qkv_b + (int64_t)(q0 + r) * ldq + h * HD + cc * 8 : qkv_b, ok ? 16u : 0u);
+    }
     load_chunk(0, 0);
     cp_async_commit();
 
-    for (int c = tid; c < ATT_BM * CPR; c += 128) {
-        const int r = c / CPR, cc = c - r * CPR;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (q0 + r < p.P) v = *reinterpret_cast<const uint4*>(qkv_b + (int64_t)(q0 + r) * ldq + h * HD + cc * 8);
-        *reinterpret_cast<uint4*>(sQ + r * LDS + cc * 8) = v;
-    }
-    __syncthreads();
-    const bool warp_active = q0 + warp * 16 < p.P;           // warps past the last query only help with the loads
+    const int qrow0 = warp * 16;                              // this warp's 16 query rows inside the tile
     uint32_t qf[HD / 16][4];
-#pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks)
-        ldmatrix_x4(qf[ks], smem_u32(sQ + (warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8));
-
     float o[HD / 8][4];
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
@@ -104,18 +105,16 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     const bool weighted = p.attn_w != nullptr && b < p.w_batch && p.n_w > 0;
     const int w_start = Nk - p.n_w;
 
-    int buf = 0;
-    for (int j0 = 0; j0 < Nk; j0 += ATT_BN, buf ^= 1) {
-        // prefetch the next chunk into the other buffer (all warps finished reading it at the end of the last iteration)
-        if (j0 + ATT_BN < Nk) load_chunk(j0 + ATT_BN, buf ^ 1);
-        cp_async_commit();
-        cp_async_wait<1>();                   // this chunk has landed (the prefetch may still be in flight)
-        __syncthreads();
-        const __half* sK = sKb + buf * ATT_BN * LDS;
-        const __half* sV = sVb + buf * ATT_BN * LDS;
-        if (warp_active) {
+    auto load_q_frags = [&]() {
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+            ldmatrix_x4(qf[ks], smem_u32(sQ + (qrow0 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8));
+    };
 
-        // ---- S = Q K^T for this warp's 16 rows x 64 keys
+    // one online-softmax pass of this warp's 16 query rows over the 64 keys j0.. held in (sK, sV)
+    auto process_chunk = [&](int j0, const __half* sK, const __half* sV) {
+        const bool full = j0 + ATT_BN <= Nk;      // warp-uniform: no key of this chunk is masked
+        // ---- S = Q K^T
         float s[ATT_BN / 8][4];
 #pragma unroll
         for (int i = 0; i < ATT_BN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
@@ -130,32 +129,41 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
                 mma_16816(s[2 * np + 1], qf[ks], kf[2], kf[3]);
             }
         }
-        // ---- scale, mask, online softmax (rows g and g+8 of the warp's 16)
+        // ---- mask, online softmax (rows g and g+8 of the warp's 16).  The running max is kept in the scaled log2
+        // domain; the 1/sqrt(hd)*log2(e) factor is folded into the exp2 argument's FFMA.
         float mx[2] = {NEG_BIG, NEG_BIG};
+        if (full) {
 #pragma unroll
-        for (int nt = 0; nt < ATT_BN / 8; ++nt) {
-            const int key = j0 + nt * 8 + 2 * t;
+            for (int nt = 0; nt < ATT_BN / 8; ++nt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const bool ok = key + (e & 1) < Nk;
-                s[nt][e] = ok ? s[nt][e] * p.scale_log2 : NEG_BIG;
-                mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+                for (int e = 0; e < 4; ++e) mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+        } else {
+#pragma unroll
+            for (int nt = 0; nt < ATT_BN / 8; ++nt) {
+                const int key = j0 + nt * 8 + 2 * t;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (key + (e & 1) >= Nk) s[nt][e] = NEG_BIG;
+                    mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+                }
             }
         }
-        float corr[2], rs[2] = {0.f, 0.f};
+        float corr[2], rs[2] = {0.f, 0.f}, msc[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-            const float m_new = fmaxf(m_run[r], mx[r]);
+            const float m_new = fmaxf(m_run[r], mx[r] * p.scale_log2);     // scale > 0: max commutes with it
             corr[r] = exp2f(m_run[r] - m_new);
             m_run[r] = m_new;
+            msc[r] = -m_new;
         }
 #pragma unroll
         for (int nt = 0; nt < ATT_BN / 8; ++nt) {
+            if (!full && j0 + (nt >> 1) * 16 >= Nk) break;      // same groups the MMAs skip
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float pv = exp2f(s[nt][e] - m_run[e >> 1]);
+                const float pv = exp2f(fmaf(s[nt][e], p.scale_log2, msc[e >> 1]));
                 rs[e >> 1] += pv;
                 s[nt][e] = pv;
             }
@@ -199,11 +207,21 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
                 mma_16816(o[2 * np + 1], a, vf[2], vf[3]);
             }
         }
-        }                                     // warp_active
-        __syncthreads();                      // everyone is done with this buffer before it is refilled
+    };
+
+    const bool warp_active = q0 + warp * 16 < p.P;       // warps past the last query only help with the loads
+    int buf = 0;
+    for (int j0 = 0; j0 < Nk; j0 += ATT_BN, buf ^= 1) {
+        // prefetch the next chunk into the other buffer (all warps finished reading it at the end of the last iteration)
+        if (j0 + ATT_BN < Nk) load_chunk(j0 + ATT_BN, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();               // this chunk has landed (the prefetch may still be in flight)
+        __syncthreads();
+        if (j0 == 0) load_q_frags();
+        if (warp_active) process_chunk(j0, sKb + buf * ATT_BN * LDS, sVb + buf * ATT_BN * LDS);
+        __syncthreads();                  // everyone is done with this buffer before it is refilled
     }
     cp_async_wait<0>();
-
     // ---- normalise and store
 #pragma unroll
     for (int r = 0; r < 2; ++r) {

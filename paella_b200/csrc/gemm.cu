@@ -13,6 +13,7 @@
 //              statistics / residual+FiLM / un-patchify scatter / NCHW transpose, vectorised global stores;
 //              overlaps with the next tile's MMAs through the second TMEM buffer.
 #include "gemm.cuh"
+#include <type_traits>
 
 #include <cstdlib>
 #include <cstring>
@@ -227,16 +228,37 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
                 const int row0 = row - lane;
                 if (row0 < M && col0 + lane < N)
                     atomicAdd(sq + (int64_t)(row0 / P) * N + col0 + lane, fx(v[0]));
-            } else if ((P & (P - 1)) == 0 && P < 32) {
-                for (int o = P >> 1; o > 0; o >>= 1) {
+            } else if (P == 16 || P == 8 || P == 4 || P == 2) {
+                // the warp's 32 rows hold 32/P whole samples: the same transpose-reduce inside aligned groups of P
+                // lanes, on 32/P sets of P columns -> lane l ends with columns {j*P + (l % P)} of its group's sample
+                // (~30 shuffles and 32/P atomics per lane instead of 32 x log2(P) shuffles and 32 atomics)
+                auto grouped = [&](auto pc) {
+                    constexpr int PP = decltype(pc)::value;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
-                }
-                if (row_ok && (lane & (P - 1)) == 0) {
+                    for (int o = PP / 2; o > 0; o >>= 1) {
+                        const bool up = (lane & o) != 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < N) atomicAdd(sq + (int64_t)(row / P) * N + col0 + j, fx(v[j]));
-                }
+                        for (int j = 0; j < 32 / PP; ++j)
+#pragma unroll
+                            for (int i = 0; i < o; ++i) {
+                                const float send = up ? v[j * PP + i] : v[j * PP + i + o];
+                                const float keep = up ? v[j * PP + i + o] : v[j * PP + i];
+                                v[j * PP + i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                            }
+                    }
+                    const int grow = row - (lane & (PP - 1));          // first row of this lane's sample
+                    if (grow < M) {
+#pragma unroll
+                        for (int j = 0; j < 32 / PP; ++j) {
+                            const int col = col0 + j * PP + (lane & (PP - 1));
+                            if (col < N) atomicAdd(sq + (int64_t)(grow / PP) * N + col, fx(v[j * PP]));
+                        }
+                    }
+                };
+                if (P == 16) grouped(std::integral_constant<int, 16>{});
+                else if (P == 8) grouped(std::integral_constant<int, 8>{});
+                else if (P == 4) grouped(std::integral_constant<int, 4>{});
+                else grouped(std::integral_constant<int, 2>{});
             } else if (row_ok) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)

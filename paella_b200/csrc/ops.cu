@@ -414,7 +414,11 @@ int launch_dwconv_ln(const float* x, const float* skip, const float* w_packed, c
     PB_CHECK(c % 8 == 0, "dwconv: c=%d must be a multiple of 8", c);
     PB_CHECK(k % 2 == 1, "dwconv: kernel_size %d must be odd", k);
     static const bool old_kernel = getenv("PB200_DWCONV_WARP") != nullptr;      // A/B knob
-    if (k == 3 && c <= 2560 && !old_kernel) return dwconv3_patch_launch(x, skip, w_packed, bias, B, h, w, c, out, st);
+    // measured (ncu, B200): the patch kernel wins at 8192 x 1280 (32.6 vs 39.6 us) and loses at 32768 x 640
+    // (99 vs 62 us: 152 registers x 160 threads leaves 15% occupancy), so it takes the wide levels only
+    static const bool patch_all = getenv("PB200_DWCONV_PATCH") != nullptr;
+    if (k == 3 && c <= 2560 && !old_kernel && (patch_all || (c > 640 && w >= DW_PW)))
+        return dwconv3_patch_launch(x, skip, w_packed, bias, B, h, w, c, out, st);
     if (c <= 128) return dwconv_dispatch<1>(x, skip, w_packed, bias, B, h, w, c, k, out, st);
     if (c <= 640) return dwconv_dispatch<5>(x, skip, w_packed, bias, B, h, w, c, k, out, st);
     if (c <= 1280) return dwconv_dispatch<10>(x, skip, w_packed, bias, B, h, w, c, k, out, st);

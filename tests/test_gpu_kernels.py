@@ -211,7 +211,8 @@ def test_gemm_plain_f32_f16(M, N, K):
     assert err16 < 2e-2, err16
 
 
-@pytest.mark.parametrize("M,N,K,P", [(512, 256, 128, 64), (8192, 5120, 1280, 64), (2048, 2560, 640, 16), (300, 128, 64, 100)])
+@pytest.mark.parametrize("M,N,K,P", [(512, 256, 128, 64), (8192, 5120, 1280, 64), (2048, 2560, 640, 16), (300, 128, 64, 100),
+                                     (256, 128, 64, 8), (384, 136, 64, 4), (128, 64, 64, 2), (2048, 5120, 1280, 16)])
 def test_gemm_gelu_sqsum(M, N, K, P):
     from paella_b200 import _lib
     ops = _ops()
