@@ -123,6 +123,49 @@ int pb200_gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64
                    const pb200_gemm_epilogue* epi, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Block-level kernels: what the reference's building-block modules (ref/src/modules.py:7-106)
+ * run when they are called on their own, outside a Paella (inside one the model executor below
+ * launches the same kernels from its plan).  Activations are channels-last rows [batch*positions, c]
+ * unless named NCHW; "16" pointers are fp16.
+ * ------------------------------------------------------------------------------------------ */
+/* nn.LayerNorm over the last dim: y = (x-mean)/sqrt(var+eps) [*weight + bias]; exactly one of out32/out16.
+ * LayerNorm2d = this between the two layout changes below   [ref/src/modules.py:22-27] */
+int pb200_layernorm(const float* x, int64_t rows, int c, float eps, const float* weight, const float* bias, float* out32,
+                    void* out16, void* stream);
+/* x.permute(0,2,3,1) / x.permute(0,3,1,2) on fp32 [batch, c, hw] <-> [batch, hw, c]   [ref/src/modules.py:27,58-61] */
+int pb200_nchw_to_nhwc(const float* in, int batch, int c, int hw, float* out, void* stream);
+int pb200_nhwc_to_nchw(const float* in, int batch, int c, int hw, float* out, void* stream);
+/* fp32 -> fp16 GEMM operand, optionally through SiLU (AttnBlock.kv_mapper[0])   [ref/src/modules.py:71-74] */
+int pb200_cast_f16(const float* x, int64_t n, int silu, void* out16, void* stream);
+/* ResBlock front: depthwise k x k conv over cat[x, skip] (groups = c, zero padding k/2) + bias + LayerNorm2d(no
+ * affine, eps 1e-6) -> fp16 [batch*h*w, c].  x fp32 NHWC [batch,h,w,c]; skip NHWC [batch,h,w,c] or NULL;
+ * w_packed fp32 [k*k][per][c] (per = 2 with skip: concatenated input channels 2g, 2g+1 feed output g)
+ * [ref/src/modules.py:46-47,57-58] */
+int pb200_dwconv_ln(const float* x, const float* skip, const float* w_packed, const float* bias, int batch, int h, int w,
+                    int c, int k, void* out16, void* stream);
+/* GlobalResponseNorm in place on the fp16 hidden [batch, rows_per_sample, n] of a PB200_EPI_GELU_F16 GEMM whose
+ * epilogue accumulated sqsum (2^-24 fixed point); zeroes zero_per_sample entries per sample of sqsum_next
+ * [ref/src/modules.py:30-40] */
+int pb200_grn_f16(void* h16, int batch, int rows_per_sample, int n, const uint64_t* sqsum, uint64_t* sqsum_next,
+                  int zero_per_sample, const float* gamma, const float* beta, void* stream);
+/* GlobalResponseNorm.forward on an fp32 NHWC tensor [batch, rows_per_sample, n]; stat = scratch [batch, n]
+ * [ref/src/modules.py:37-40] */
+int pb200_grn_f32(const float* x, int batch, int rows_per_sample, int n, const float* gamma, const float* beta, float* stat,
+                  float* out, void* stream);
+/* TimestepBlock: x[r, j] = x*(1 + film[r/rows_per_sample, film_off + j]) + film[.., film_off + n + j] in place
+ * [ref/src/modules.py:104-106] */
+int pb200_film_apply(float* x, int64_t rows, int n, int rows_per_sample, const float* film, int64_t film_ld, int64_t film_off,
+                     void* stream);
+/* Attention core of nn.MultiheadAttention / CustomMultiheadAttention after the in-projection:
+ * qkv16 [batch*positions, 3*embed] = q | k_self | v_self, ckv16 [batch, s_max, 2*embed] = k_cond | v_cond
+ * (kv_len[batch] valid rows, NULL = s_max); keys = [self ; cond] if self_attn else cond; optional post-softmax
+ * attn_weights on the last n_weights keys of samples [0, weighted_batch); out16 [batch*positions, embed]
+ * [ref/src/modules.py:12-19, ref/utils/alter_attention.py:19-36] */
+int pb200_attention(const void* qkv16, const void* ckv16, const int* kv_len, void* out16, int batch, int positions, int s_max,
+                    int embed, int nhead, int self_attn, const float* attn_weights, int n_weights, int weighted_batch,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Denoiser (ref/src/modules.py:109-283, ref/utils/modules.py) as an opaque handle.
  * ------------------------------------------------------------------------------------------ */
 #define PB200_MAX_LEVELS 4

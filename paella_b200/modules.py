@@ -21,12 +21,81 @@ from ._lib import PaellaB200Error, check, current_stream, lib, ptr
 
 
 # ------------------------------------------------------------------------------------------------
-# Building blocks — parameter layout of ref/src/modules.py:7-106
+# Building blocks — parameter layout AND stand-alone forward of ref/src/modules.py:7-106.
+# Inside a Paella the blocks are executed by the fused plan in csrc/paella_model.cu; called on their own
+# they compose the same kernels through the block-level C ABI (include/paella_b200.h).  Inference
+# semantics (Dropout = identity), fp16 GEMM operands / fp32 accumulation like the model path.
 # ------------------------------------------------------------------------------------------------
-def _standalone_forward_error(name: str):
-    raise PaellaB200Error(
-        f"{name}.forward outside a Paella model is not wired to the CUDA library yet; "
-        "blocks are executed by Paella.forward's fused plan (no PyTorch fallback exists).")
+def _cached(mod: nn.Module, key: str, src: torch.Tensor, make):
+    """Derived copy (fp16 cast / repack) of a parameter, rebuilt when the parameter changes."""
+    cache = mod.__dict__.setdefault("_pb200_cache", {})
+    tag = (src.data_ptr(), src._version, str(src.device))
+    hit = cache.get(key)
+    if hit is None or hit[0] != tag:
+        with torch.no_grad():
+            hit = (tag, make(src.detach()))
+        cache[key] = hit
+    return hit[1]
+
+
+def _w16(mod, key, w):
+    return _cached(mod, key, w, lambda t: t.reshape(t.shape[0], -1).to(torch.float16).contiguous())
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().float().contiguous()
+
+
+def _to_rows(x: torch.Tensor) -> torch.Tensor:
+    """NCHW fp32 -> channels-last rows [B*H*W, C] (a fresh buffer the block may update in place)."""
+    if x.dim() != 4:
+        raise PaellaB200Error(f"expected an NCHW tensor, got shape {tuple(x.shape)}")
+    x = _f32(x)
+    B, C, H, W = x.shape
+    out = torch.empty(B * H * W, C, dtype=torch.float32, device=x.device)
+    check(lib().pb200_nchw_to_nhwc(ptr(x), B, C, H * W, ptr(out), current_stream()), "pb200_nchw_to_nhwc")
+    return out
+
+
+def _to_nchw(rows: torch.Tensor, shape) -> torch.Tensor:
+    B, C, H, W = shape
+    out = torch.empty(B, C, H, W, dtype=torch.float32, device=rows.device)
+    check(lib().pb200_nhwc_to_nchw(ptr(rows), B, C, H * W, ptr(out), current_stream()), "pb200_nhwc_to_nchw")
+    return out
+
+
+def _cast16(x: torch.Tensor, silu: bool = False) -> torch.Tensor:
+    x = _f32(x)
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    check(lib().pb200_cast_f16(ptr(x), x.numel(), int(silu), ptr(out), current_stream()), "pb200_cast_f16")
+    return out
+
+
+def _layernorm(rows: torch.Tensor, ln: nn.LayerNorm, half: bool) -> torch.Tensor:
+    M, C = rows.shape
+    if tuple(ln.normalized_shape) != (C,):
+        raise PaellaB200Error(f"LayerNorm over {tuple(ln.normalized_shape)} applied to {C} channels")
+    out = torch.empty(M, C, dtype=torch.float16 if half else torch.float32, device=rows.device)
+    w = _f32(ln.weight) if ln.weight is not None else None
+    b = _f32(ln.bias) if ln.bias is not None else None
+    check(lib().pb200_layernorm(ptr(rows), M, C, float(ln.eps), ptr(w), ptr(b), None if half else ptr(out),
+                                ptr(out) if half else None, current_stream()), "pb200_layernorm")
+    return out
+
+
+def _mlp_rows(mlp: nn.Sequential, a16: torch.Tensor, resid_rows: torch.Tensor, batch: int) -> torch.Tensor:
+    """channelwise = Linear -> GELU -> GRN -> Dropout(eval) -> Linear, added onto resid_rows in place."""
+    lin1, grn, lin2 = mlp[0], mlp[2], mlp[4]
+    M, c = a16.shape
+    n = lin1.out_features
+    P = M // batch
+    h16 = torch.empty(M, n, dtype=torch.float16, device=a16.device)
+    sq = torch.zeros(2, batch, n, dtype=torch.int64, device=a16.device)
+    ops.gemm_f16(a16, _w16(lin1, "w16", lin1.weight), _lib.EPI_GELU_F16, h16, bias=_f32(lin1.bias), sqsum=sq[0], rows_per_sample=P)
+    check(lib().pb200_grn_f16(ptr(h16), batch, P, n, ptr(sq[0]), ptr(sq[1]), n, ptr(_f32(grn.gamma).view(-1)),
+                              ptr(_f32(grn.beta).view(-1)), current_stream()), "pb200_grn_f16")
+    ops.gemm_f16(h16, _w16(lin2, "w16", lin2.weight), _lib.EPI_RESID_F32, resid_rows, bias=_f32(lin2.bias), resid=resid_rows)
+    return resid_rows
 
 
 class Attention2D(nn.Module):
@@ -36,8 +105,38 @@ class Attention2D(nn.Module):
         super().__init__()
         self.attn = torch.nn.MultiheadAttention(c, nhead, dropout=dropout, bias=True, batch_first=True)
 
+    def _core(self, xq16: torch.Tensor, kv16: torch.Tensor, batch: int, self_attn: bool, attn_weights=None) -> torch.Tensor:
+        """in-projection + attention core: xq16 [B*P, E] queries (and self keys), kv16 [B*S, E] -> fp16 [B*P, E]."""
+        mha = self.attn
+        E = mha.embed_dim
+        M = xq16.shape[0]
+        P = M // batch
+        S = kv16.shape[0] // batch if kv16 is not None else 0
+        w16 = _w16(mha, "in16", mha.in_proj_weight)
+        b32 = _f32(mha.in_proj_bias)
+        qkv = torch.empty(M, 3 * E, dtype=torch.float16, device=xq16.device)
+        ops.gemm_f16(xq16, w16, _lib.EPI_F16, qkv, bias=b32)
+        ckv = None
+        if S > 0:
+            ckv = torch.empty(batch * S, 2 * E, dtype=torch.float16, device=xq16.device)
+            ops.gemm_f16(kv16, w16[E:], _lib.EPI_F16, ckv, bias=b32[E:])
+        aw, n_w = None, 0
+        if attn_weights is not None:
+            aw = _f32(attn_weights).reshape(-1)
+            n_w = aw.numel()
+        out = torch.empty(M, E, dtype=torch.float16, device=xq16.device)
+        check(lib().pb200_attention(ptr(qkv), ptr(ckv), None, ptr(out), batch, P, S, E, mha.num_heads, int(bool(self_attn)),
+                                    ptr(aw), n_w, batch, current_stream()), "pb200_attention")
+        return out
+
     def forward(self, x, kv, self_attn=False, **kwargs):
-        _standalone_forward_error("Attention2D")
+        B, C = x.shape[0], x.shape[1]
+        rows16 = _cast16(_to_rows(x))
+        kv16 = _cast16(kv).view(-1, C) if kv is not None and kv.numel() > 0 else None
+        o16 = self._core(rows16, kv16, B, self_attn, kwargs.get("attn_weights"))
+        out = torch.empty(rows16.shape[0], C, dtype=torch.float32, device=x.device)
+        ops.gemm_f16(o16, _w16(self.attn, "out16", self.attn.out_proj.weight), _lib.EPI_F32, out, bias=_f32(self.attn.out_proj.bias))
+        return _to_nchw(out, x.shape)
 
 
 class LayerNorm2d(nn.LayerNorm):
@@ -47,11 +146,11 @@ class LayerNorm2d(nn.LayerNorm):
         super().__init__(*args, **kwargs)
 
     def forward(self, x):
-        _standalone_forward_error("LayerNorm2d")
+        return _to_nchw(_layernorm(_to_rows(x), self, half=False), x.shape)
 
 
 class GlobalResponseNorm(nn.Module):
-    """ref/src/modules.py:30-40."""
+    """ref/src/modules.py:30-40 (input NHWC ``[B, H, W, dim]``)."""
 
     def __init__(self, dim):
         super().__init__()
@@ -59,7 +158,15 @@ class GlobalResponseNorm(nn.Module):
         self.beta = nn.Parameter(torch.zeros(1, 1, 1, dim))
 
     def forward(self, x):
-        _standalone_forward_error("GlobalResponseNorm")
+        if x.dim() != 4 or x.shape[-1] != self.gamma.shape[-1]:
+            raise PaellaB200Error(f"GlobalResponseNorm({self.gamma.shape[-1]}) got shape {tuple(x.shape)}")
+        x = _f32(x)
+        B, H, W, N = x.shape
+        out = torch.empty_like(x)
+        stat = torch.empty(B, N, dtype=torch.float32, device=x.device)
+        check(lib().pb200_grn_f32(ptr(x), B, H * W, N, ptr(_f32(self.gamma).view(-1)), ptr(_f32(self.beta).view(-1)), ptr(stat),
+                                  ptr(out), current_stream()), "pb200_grn_f32")
+        return out
 
 
 def _mlp_holder(c, dropout):
@@ -77,11 +184,25 @@ class ResBlock(nn.Module):
         self.channelwise = _mlp_holder(c, dropout)
 
     def forward(self, x, x_skip=None):
-        _standalone_forward_error("ResBlock")
+        dw = self.depthwise
+        c, per, k = dw.out_channels, dw.in_channels // dw.out_channels, dw.kernel_size[0]
+        if per not in (1, 2) or dw.in_channels != per * c or (x_skip is not None) != (per == 2):
+            raise PaellaB200Error("ResBlock: c_skip must be 0 (no x_skip) or c (with x_skip)")
+        if self.norm.elementwise_affine or self.norm.eps != 1e-6:
+            raise PaellaB200Error("ResBlock: the fused depthwise+LayerNorm kernel is eps=1e-6 without affine (the reference's setting)")
+        B, _, H, W = x.shape
+        rows = _to_rows(x)
+        skip = _to_rows(x_skip) if x_skip is not None else None
+        # [c, per, k, k] -> [k*k][per][c]; with a skip the conv input is cat[x, x_skip], group g reads channels 2g, 2g+1
+        wp = _cached(dw, "wp", dw.weight, lambda t: t.float().permute(2, 3, 1, 0).reshape(k * k, per, c).contiguous())
+        a16 = torch.empty(B * H * W, c, dtype=torch.float16, device=x.device)
+        check(lib().pb200_dwconv_ln(ptr(rows), ptr(skip), ptr(wp), ptr(_f32(dw.bias)), B, H, W, c, k, ptr(a16), current_stream()),
+              "pb200_dwconv_ln")
+        return _to_nchw(_mlp_rows(self.channelwise, a16, rows, B), x.shape)
 
 
 class AttnBlock(nn.Module):
-    """ref/src/modules.py:65-79."""
+    """ref/src/modules.py:65-79 (``attn_weights=`` as in ref/utils/modules.py:76-78)."""
 
     def __init__(self, c, c_cond, nhead, self_attn=True, dropout=0.0):
         super().__init__()
@@ -91,7 +212,19 @@ class AttnBlock(nn.Module):
         self.kv_mapper = nn.Sequential(nn.SiLU(), nn.Linear(c_cond, c))
 
     def forward(self, x, kv, **kwargs):
-        _standalone_forward_error("AttnBlock")
+        B, C = x.shape[0], x.shape[1]
+        rows = _to_rows(x)
+        xn16 = _layernorm(rows, self.norm, half=True)
+        lin = self.kv_mapper[1]
+        kv16 = None
+        if kv is not None and kv.numel() > 0:
+            s16 = _cast16(kv, silu=True).view(-1, lin.in_features)
+            kv16 = torch.empty(s16.shape[0], C, dtype=torch.float16, device=x.device)
+            ops.gemm_f16(s16, _w16(lin, "w16", lin.weight), _lib.EPI_F16, kv16, bias=_f32(lin.bias))
+        o16 = self.attention._core(xn16, kv16, B, self.self_attn, kwargs.get("attn_weights"))
+        mha = self.attention.attn
+        ops.gemm_f16(o16, _w16(mha, "out16", mha.out_proj.weight), _lib.EPI_RESID_F32, rows, bias=_f32(mha.out_proj.bias), resid=rows)
+        return _to_nchw(rows, x.shape)
 
 
 class FeedForwardBlock(nn.Module):
@@ -103,7 +236,8 @@ class FeedForwardBlock(nn.Module):
         self.channelwise = _mlp_holder(c, dropout)
 
     def forward(self, x):
-        _standalone_forward_error("FeedForwardBlock")
+        rows = _to_rows(x)
+        return _to_nchw(_mlp_rows(self.channelwise, _layernorm(rows, self.norm, half=True), rows, x.shape[0]), x.shape)
 
 
 class TimestepBlock(nn.Module):
@@ -114,7 +248,12 @@ class TimestepBlock(nn.Module):
         self.mapper = nn.Linear(c_timestep, c * 2)
 
     def forward(self, x, t):
-        _standalone_forward_error("TimestepBlock")
+        B, C, H, W = x.shape
+        film = torch.empty(B, 2 * C, dtype=torch.float32, device=x.device)
+        ops.gemm_f16(_cast16(t).view(B, -1), _w16(self.mapper, "w16", self.mapper.weight), _lib.EPI_F32, film, bias=_f32(self.mapper.bias))
+        rows = _to_rows(x)
+        check(lib().pb200_film_apply(ptr(rows), B * H * W, C, H * W, ptr(film), 2 * C, 0, current_stream()), "pb200_film_apply")
+        return _to_nchw(rows, x.shape)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -99,3 +99,9 @@ def test_cpu_tensors_raise_not_fallback():
     from paella_b200 import _lib, ops
     with pytest.raises(_lib.PaellaB200Error):
         ops.vq_nearest(torch.zeros(4, 4), torch.zeros(8, 4))
+    # the stand-alone building blocks go through the same boundary
+    from paella_b200.modules import LayerNorm2d, ResBlock
+    with pytest.raises(_lib.PaellaB200Error):
+        ResBlock(32)(torch.zeros(1, 32, 4, 4))
+    with pytest.raises(_lib.PaellaB200Error):
+        LayerNorm2d(32)(torch.zeros(1, 32, 4, 4))
