@@ -97,6 +97,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant (GEMM) kernels from the committed `ncu --set full` capture: the
+    launch-weighted mean over the main-path shapes of one forward (bench.py cannot run ncu itself)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_traffic.json")
+    try:
+        ks = json.load(open(path))["kernels"]
+        n = sum(k["launches_per_forward"] for k in ks)
+        mean = sum(k["launches_per_forward"] * k["dram_bytes"] for k in ks) / n
+        alg = sum(k["launches_per_forward"] * k["algorithmic_bytes"] for k in ks) / n
+        return mean, f"profiles/r01_ncu_traffic.json (launch-weighted mean of {len(ks)} shapes; algorithmic {alg / 1e6:.0f} MB)"
+    except (OSError, KeyError, ValueError, ZeroDivisionError):
+        return None, None
+
+
 def build_model(device):
     from paella_b200.modules import Paella
     from paella_b200.synth import rerandomize_
@@ -254,8 +268,10 @@ def main():
     gemm_n = sum(v["launches"] for k, v in prof.items() if k.startswith("gemm") or k == "fused_sampler")
     total_ms = sum(v["ms"] for v in prof.values())
     achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic()
     roofline = {"bound": "tensor", "kernel": "gemm_f16_kernel (tcgen05 GEMM family incl. fused sampler)", "achieved": achieved,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": pk["src"] + " bf16 sustained", "launches_per_step": gemm_n,
                 "avg_launch_ms": gemm_ms / max(gemm_n, 1), "share_of_step": gemm_ms / total_ms if total_ms else None,
                 "families": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],

@@ -172,9 +172,18 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, int M, int N, int row, int col0,
                                                float (&v)[32], int lane, const EpiPre<MODE>& pre) {
     const bool row_ok = row < M;
+    // warp-uniform: no column / row of this chunk is out of range -> the hot path carries no per-element predicates
+    const bool full_cols = col0 + 32 <= N;
+    const bool full = full_cols && __all_sync(0xffffffffu, row_ok);
     // ---- bias (indexed by GEMM column in every mode)
-    {
-        if (ep.bias) {
+    if (ep.bias) {
+        if (full_cols) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + g * 4));
+                v[g * 4 + 0] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
+            }
+        } else {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 if (col0 + g * 4 < N) {
@@ -211,8 +220,13 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
             unsigned long long* sq = reinterpret_cast<unsigned long long*>(ep.sqsum);
             auto fx = [](float x) { return (unsigned long long)__float2ull_rn(x * 16777216.0f); };
             const int P = ep.rows_per_sample;
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (row_ok && col0 + j < N) ? v[j] * v[j] : 0.f;
+                for (int j = 0; j < 32; ++j) v[j] *= v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = (row_ok && col0 + j < N) ? v[j] * v[j] : 0.f;
+            }
             if ((P & 31) == 0) {
                 // transpose-reduce over the warp's 32 rows: lane j ends with the column-(col0+j) sum
 #pragma unroll
