@@ -225,8 +225,11 @@ int pb200_paella_c_embeddings(pb200_paella* m, const pb200_cond* cond, int batch
 /* Paella.forward up to out_mapper's LayerNorm: tokens int64 [Bt,H,W], r fp32 [Bt] ->
  * features fp32 [Bt*H*W, c_out] (rows (b,y,x)).  attn_weights fp32 [n_attn_weights] or NULL scales
  * the last n key columns after the softmax for samples [0, attn_weights_batch)
- * (ref/utils/alter_attention.py:23-34; the notebook passes it on the conditional forward only). */
-int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r, int batch_total, int h, int w,
+ * (ref/utils/alter_attention.py:23-34; the notebook passes it on the conditional forward only).
+ * cfg_pairs = 1: the classifier-free-guidance batch of ref/src/utils.py:42-45 -- tokens [Bt/2,H,W] and r [Bt/2] are
+ * given once, sample i + Bt/2 is sample i under the unconditional rows of the conditioning cache.  The blocks before
+ * the first AttnBlock do not see the conditioning and are evaluated once per pair (identical arithmetic). */
+int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r, int batch_total, int cfg_pairs, int h, int w,
                           const void* cond_cache, int s_max, const float* attn_weights, int n_attn_weights,
                           int attn_weights_batch, float* features, void* workspace, int64_t workspace_bytes,
                           void* stream);
@@ -242,9 +245,6 @@ int pb200_paella_logits(pb200_paella* m, const float* features, int batch, int h
 int pb200_paella_sample_tokens(pb200_paella* m, const float* features, int batch, int hw, int cfg_on, double cfg,
                                double temperature, uint64_t seed, uint64_t offset, int64_t* tokens_out,
                                void* workspace, int64_t workspace_bytes, void* stream);
-
-/* Standalone blocks for the module-level API (Attention2D/ResBlock/... used outside a Paella):
- * executed by a 1-level Paella plan; see paella_b200/modules.py. */
 
 /* ------------------------------------------------------------------------------------------
  * VQGAN (ref/src/vqgan.py:45-107).

@@ -531,7 +531,7 @@ int pb200_paella_prepare_cond(pb200_paella* m, const pb200_cond* cond, int batch
     return 0;
 }
 
-int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r, int batch_total, int h, int w,
+int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r, int batch_total, int cfg_pairs, int h, int w,
                           const void* cond_cache, int s_max, const float* attn_weights, int n_attn_weights,
                           int attn_weights_batch, float* features, void* workspace, int64_t workspace_bytes,
                           void* stream) {
@@ -550,39 +550,58 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
     const int* kv_len = reinterpret_cast<const int*>(cache + cond_block_off(m, m->n_attn, Bt, s_max));
 
     int gh[PB200_MAX_LEVELS], gw[PB200_MAX_LEVELS];
-    int64_t Ml[PB200_MAX_LEVELS];
-    for (int l = 0; l < L; ++l) {
-        gh[l] = (h / ps) >> l; gw[l] = (w / ps) >> l;
-        Ml[l] = (int64_t)Bt * gh[l] * gw[l];
-    }
+    for (int l = 0; l < L; ++l) { gh[l] = (h / ps) >> l; gw[l] = (w / ps) >> l; }
+
+    // Classifier-free-guidance pairs: sample i and sample i + Bt/2 carry the same (tokens, r) and differ only in their
+    // conditioning rows, which enter through the AttnBlocks alone.  Everything before the first AttnBlock (the whole
+    // level-0 down stack of the reference config, 'CT') is therefore computed ONCE for Bt/2 samples and replicated
+    // when the first AttnBlock is reached -- the same arithmetic on the same inputs, not an approximation.
+    PB_CHECK(!cfg_pairs || Bt % 2 == 0, "features: cfg_pairs needs an even batch_total (got %d)", Bt);
+    int Bc = cfg_pairs ? Bt / 2 : Bt;                   // samples currently carried by x
 
     // timestep embedding and every TimestepBlock's (a, b) at once
-    PB_TRY(launch_r_embed(r, Bt, c.c_r, ws.r_emb, st));
-    PB_TRY(launch_film_table(ws.r_emb, Bt, c.c_r, m->w<float>(m->film_w), m->w<float>(m->film_b), m->film_total, ws.film, st));
+    PB_TRY(launch_r_embed(r, Bc, c.c_r, ws.r_emb, st));
+    PB_TRY(launch_film_table(ws.r_emb, Bc, c.c_r, m->w<float>(m->film_w), m->w<float>(m->film_b), m->film_total, ws.film, st));
+    if (Bc < Bt)
+        PB_CUDA(cudaMemcpyAsync(ws.film + (size_t)Bc * m->film_total, ws.film, (size_t)Bc * m->film_total * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st));
     PB_CUDA(cudaMemsetAsync(ws.gsq, 0, (size_t)Bt * 4 * m->max_c * sizeof(uint64_t), st));
+    if (Bc < Bt) PB_CUDA(cudaMemsetAsync(ws.gscale, 0, (size_t)Bt * 4 * m->max_c * sizeof(uint64_t), st));
     uint64_t* grn_stat[2] = {ws.gsq, ws.gscale};      // ping-pong: the GRN kernel of block i zeroes the buffer of block i+1
     int grn_flip = 0;
 
     // in_mapper + embedding
-    PB_TRY(launch_embed_tokens(tokens, m->w<float>(m->emb_table), c.num_labels, c.c_in, Bt, h, w, ps, ws.h16, st));
+    PB_TRY(launch_embed_tokens(tokens, m->w<float>(m->emb_table), c.num_labels, c.c_in, Bc, h, w, ps, ws.h16, st));
     {
+        const int64_t M0 = (int64_t)Bc * gh[0] * gw[0];
         pb200_gemm_epilogue e = epi(PB200_EPI_F32, m->w<float>(m->emb_b), ws.xd[0], c.c_hidden[0]);
-        PB_TRY(m->gemm(ws.h16, (int64_t)c.c_in * ps * ps, Ml[0], (int64_t)c.c_in * ps * ps, m->emb_w, c.c_hidden[0], e, st));
-        PB_TRY(launch_ln_rows(ws.xd[0], Ml[0], c.c_hidden[0], 1.0f, 0.0f, nullptr, ws.xd[0], st));
+        PB_TRY(m->gemm(ws.h16, (int64_t)c.c_in * ps * ps, M0, (int64_t)c.c_in * ps * ps, m->emb_w, c.c_hidden[0], e, st));
+        PB_TRY(launch_ln_rows(ws.xd[0], M0, c.c_hidden[0], 1.0f, 0.0f, nullptr, ws.xd[0], st));
     }
 
     float* x = ws.xd[0];
     bool up_phase = false;
+    // replicate the shared prefix: x (= xd[l] on the down path) and every saved level output below it
+    auto replicate = [&](int level) -> int {
+        for (int q = 0; q <= level; ++q) {
+            const size_t n = (size_t)Bc * gh[q] * gw[q] * c.c_hidden[q];
+            PB_CUDA(cudaMemcpyAsync(ws.xd[q] + n, ws.xd[q], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        Bc = Bt;
+        return 0;
+    };
     for (size_t bi = 0; bi < m->blocks.size(); ++bi) {
         const BlockPlan& b = m->blocks[bi];
         const int l = b.level, ch = b.c, P = gh[l] * gw[l];
-        const int64_t M = Ml[l];
+        // the prefix ends at the first AttnBlock, or where the up path starts (its tensors live outside xd[])
+        if (Bc < Bt && (b.kind == BK_ATTN || b.kind == BK_UP || (b.kind == BK_SAVE && l == L - 1))) PB_TRY(replicate(l));
+        const int64_t M = (int64_t)Bc * P;
         switch (b.kind) {
             case BK_SAVE:
                 if (l == L - 1) up_phase = true;       // deepest level: the up path continues on the same tensor
                 break;
             case BK_DOWN: {
-                PB_TRY(launch_ln_patchify2(x, Bt, gh[l - 1], gw[l - 1], c.c_hidden[l - 1], ws.a16, st));
+                PB_TRY(launch_ln_patchify2(x, Bc, gh[l - 1], gw[l - 1], c.c_hidden[l - 1], ws.a16, st));
                 pb200_gemm_epilogue e = epi(PB200_EPI_F32, m->w<float>(b.rs_b), ws.xd[l], ch);
                 PB_TRY(m->gemm(ws.a16, 4 * (int64_t)c.c_hidden[l - 1], M, 4 * (int64_t)c.c_hidden[l - 1], b.rs_w, ch, e, st));
                 x = ws.xd[l];
@@ -601,7 +620,7 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
             case BK_FF: {
                 if (b.kind == BK_RES) {
                     const float* skip = b.c_skip ? ws.xd[l] : nullptr;
-                    PB_TRY(launch_dwconv_ln(x, skip, m->w<float>(b.dw_w), m->w<float>(b.dw_b), Bt, gh[l], gw[l], ch,
+                    PB_TRY(launch_dwconv_ln(x, skip, m->w<float>(b.dw_w), m->w<float>(b.dw_b), Bc, gh[l], gw[l], ch,
                                             c.kernel_size, ws.a16, st));
                 } else {
                     PB_TRY(launch_ln_rows(x, M, ch, 1.0f, 0.0f, ws.a16, nullptr, st));
@@ -612,7 +631,7 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
                 grn_flip ^= 1;
                 e1.sqsum = stat; e1.rows_per_sample = P;
                 PB_TRY(m->gemm(ws.a16, ch, M, ch, b.w1, 4 * (int64_t)ch, e1, st));
-                PB_TRY(launch_grn_fused(ws.h16, Bt, P, 4 * ch, stat, stat_next, 4 * m->max_c, m->w<float>(b.gamma), m->w<float>(b.beta), st));
+                PB_TRY(launch_grn_fused(ws.h16, Bc, P, 4 * ch, stat, stat_next, 4 * m->max_c, m->w<float>(b.gamma), m->w<float>(b.beta), st));
                 pb200_gemm_epilogue e2 = epi(PB200_EPI_RESID_F32, m->w<float>(b.b2), x, ch);
                 e2.resid = x; e2.ldr = ch; e2.rows_per_sample = P;
                 if (b.film_off >= 0) { e2.film = ws.film; e2.film_ld = m->film_total; e2.film_off = b.film_off; }
@@ -647,11 +666,16 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
     // clf (LN2d, 1x1 conv, PixelShuffle) + out_mapper's LayerNorm2d
     {
         const int ch = c.c_hidden[0];
-        PB_TRY(launch_ln_rows(x, Ml[0], ch, 1.0f, 0.0f, ws.a16, nullptr, st));
+        const int64_t M0 = (int64_t)Bc * gh[0] * gw[0];
+        PB_TRY(launch_ln_rows(x, M0, ch, 1.0f, 0.0f, ws.a16, nullptr, st));
         pb200_gemm_epilogue e = epi(PB200_EPI_UNPATCH_F32, m->w<float>(m->clf_b), ws.y, 0);
         e.up_h = gh[0]; e.up_w = gw[0]; e.up_cout = c.c_out;
-        PB_TRY(m->gemm(ws.a16, ch, Ml[0], ch, m->clf_w, 4 * (int64_t)c.c_out, e, st));
-        PB_TRY(launch_ln_rows(ws.y, (int64_t)Bt * h * w, c.c_out, 1.0f, 0.0f, nullptr, features, st));
+        PB_TRY(m->gemm(ws.a16, ch, M0, ch, m->clf_w, 4 * (int64_t)c.c_out, e, st));
+        PB_TRY(launch_ln_rows(ws.y, (int64_t)Bc * h * w, c.c_out, 1.0f, 0.0f, nullptr, features, st));
+        if (Bc < Bt) {      // a model without any AttnBlock or up path: the two halves are identical to the end
+            const size_t n = (size_t)Bc * h * w * c.c_out;
+            PB_CUDA(cudaMemcpyAsync(features + n, features, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
     }
     return 0;
 }

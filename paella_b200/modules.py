@@ -515,12 +515,18 @@ class Paella(nn.Module):
 
     # -------------------------------------------------------------- forward pieces
     def features(self, x: torch.Tensor, r: torch.Tensor, cond: ConditioningCache, attn_weights=None,
-                 attn_weights_batch: int = 0) -> torch.Tensor:
-        """Everything up to out_mapper's LayerNorm: tokens [Bt,H,W] -> fp32 [Bt*H*W, c_out]."""
+                 attn_weights_batch: int = 0, cfg_pairs: bool = False) -> torch.Tensor:
+        """Everything up to out_mapper's LayerNorm: tokens [Bt,H,W] -> fp32 [Bt*H*W, c_out].
+
+        ``cfg_pairs=True``: x [B,H,W] and r [B] are the classifier-free-guidance batch of ref/src/utils.py:42-45 —
+        evaluated under the conditional rows [0,B) and the unconditional rows [B,2B) of ``cond``; the result has 2B
+        samples, and the conditioning-independent blocks before the first AttnBlock run once per pair."""
         self._ensure_packed()
         L = lib()
         dev = self._device()
         Bt, H, W = x.shape
+        if cfg_pairs:
+            Bt *= 2
         if Bt != cond.batch_total:
             raise PaellaB200Error(f"batch {Bt} does not match the conditioning cache ({cond.batch_total})")
         with torch.cuda.device(dev):
@@ -529,7 +535,7 @@ class Paella(nn.Module):
             ws = self._ws(L.pb200_paella_workspace_bytes(self._handle, Bt, H, W, cond.s_max))
             feats = torch.empty(Bt * H * W, self._cfg["c_out"], dtype=torch.float32, device=dev)
             aw = attn_weights.to(device=dev, dtype=torch.float32).contiguous() if attn_weights is not None else None
-            check(L.pb200_paella_features(self._handle, ptr(x), ptr(r), Bt, H, W, ptr(cond.cache), cond.s_max, ptr(aw),
+            check(L.pb200_paella_features(self._handle, ptr(x), ptr(r), Bt, int(cfg_pairs), H, W, ptr(cond.cache), cond.s_max, ptr(aw),
                                           aw.numel() if aw is not None else 0, attn_weights_batch, ptr(feats), ptr(ws),
                                           ws.numel(), current_stream()), "pb200_paella_features")
         return feats

@@ -46,8 +46,7 @@ def _sample_core(model: Paella, model_inputs, latent_shape, unconditional_inputs
             guided = use_cfg_any and i < sampling_conditional_steps
             t = float(t_list[i])
             if guided:
-                cond = cond_full
-                tokens = torch.cat([sampled, sampled], dim=0)
+                cond, tokens = cond_full, sampled          # one (tokens, r) per CFG pair, see Paella.features
             elif use_cfg_any:
                 if cond_only is None:
                     cond_only = model.prepare_conditioning([model_inputs], (H, W))
@@ -55,7 +54,7 @@ def _sample_core(model: Paella, model_inputs, latent_shape, unconditional_inputs
             else:
                 cond, tokens = cond_full, sampled
             r = torch.full((tokens.shape[0],), t, dtype=torch.float32, device=dev)
-            feats = model.features(tokens, r, cond, attn_weights, B if attn_weights is not None else 0)
+            feats = model.features(tokens, r, cond, attn_weights, B if attn_weights is not None else 0, cfg_pairs=guided)
             cfg_i = float(cfgs[i]) if guided else None
             if mode == "multinomial" and not exact:
                 sampled = model.sample_tokens(feats, B, H, W, cfg_i, float(temperatures[i]))

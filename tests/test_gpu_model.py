@@ -232,6 +232,25 @@ def test_default_config_sample_runs_and_is_seed_deterministic(default_model):
     assert same > 0.999         # bit-identical RNG stream and order-independent (integer) GRN statistics
 
 
+@pytest.mark.parametrize("which", ["tiny", "default"])
+def test_cfg_pairs_prefix_sharing_is_exact(which, tiny, default_model):
+    """The CFG batch evaluated with one (tokens, r) per pair (blocks before the first AttnBlock run once) must equal
+    the plain 2B-sample forward bit for bit: it is the same arithmetic on the same inputs."""
+    from paella_b200.synth import synthetic_conditioning
+    m = tiny[0] if which == "tiny" else default_model[0]
+    B, L = 3, 16
+    kw = dict(byt5_embd=m.byt5_mapper.in_features, clip_embd=m.clip_mapper.in_features)
+    cond, uncond = synthetic_conditioning(B, L, device=DEV, **kw)
+    cache = m.prepare_conditioning([cond, uncond], (16, 16))
+    x = torch.randint(0, m.num_labels, (B, 16, 16), device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    r = torch.tensor([0.9, 0.5, 0.1], device=DEV)
+    full = m.features(torch.cat([x, x]), torch.cat([r, r]), cache)
+    paired = m.features(x, r, cache, cfg_pairs=True)
+    assert paired.shape == full.shape
+    assert torch.equal(paired, full)
+    assert not torch.equal(full[: full.shape[0] // 2], full[full.shape[0] // 2:])       # the two halves do differ
+
+
 def test_notebook_sampler_modes_and_intermediates(tiny):
     """paella_inference.ipynb cell-3 signature: modes multinomial / argmax / quant, sampling_quant_steps, attn_weights,
     init_x, sampling_conditional_steps; returns (sampled, intermediates) with one entry per resample and per renoise."""
