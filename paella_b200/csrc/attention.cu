@@ -39,13 +39,11 @@ constexpr int ATT_BN = 64;   // keys per chunk
 constexpr float NEG_BIG = -1e30f;
 
 // One CTA per (64 queries, head, sample); each warp owns 16 queries and walks the keys in 64-key chunks
-// (double-buffered cp.async).
-// KS = 4 (levels with <= 16 queries per sample, e.g. the 4x4 grid of a 32x32 latent): a 64-query tile would idle three
-// of the four warps, so the warps split the KEYS of every chunk instead -- warp w runs the online softmax over the 16-key
-// group w of each chunk for the same 16 queries (same loads, same shared memory), and the four partial (max, sum, O)
-// triples are merged through shared memory at the end.  (Loading all chunks up front and giving each warp a whole
-// chunk was tried first and lost: more shared memory, no load/compute overlap.)
-template <int HD, int KS>
+// (double-buffered cp.async).  Tried on B200 and dropped, twice: splitting the KEYS over the warps for the <= 16-query
+// levels -- (a) whole chunks per warp, all chunks resident: 20.7 vs 19.6 ms per bench step (the extra shared memory costs
+// a resident CTA); (b) the 16-key groups of every chunk per warp, same loads: 19.9 vs 19.5 ms.  Those launches are bound
+// by the K/V load latency (86 MB of conditioning K/V per launch), not by the one busy warp.
+template <int HD>
 __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     constexpr int LDS = HD + 8;           // padded row: (HD+8)*2 bytes is an odd multiple of 16 -> conflict-free ldmatrix
     constexpr int CPR = HD / 8;           // 16-byte chunks per row
@@ -58,7 +56,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int q0 = blockIdx.x * (KS == 4 ? 16 : QROWS), h = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * QROWS, h = blockIdx.y, b = blockIdx.z;
     const int E = p.E;
     const int64_t ldq = 3 * (int64_t)E, ldc = 2 * (int64_t)E;
     const int n_self = p.self_attn ? p.P : 0;
@@ -99,9 +97,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     load_chunk(0, 0);
     cp_async_commit();
 
-    const int qrow0 = KS == 4 ? 0 : warp * 16;                // this warp's 16 query rows inside the tile
-    constexpr int NG = 4 / KS;                                // 16-key groups of a chunk this warp handles ...
-    const int kofs = KS == 4 ? warp * 16 : 0;                 // ... starting at this key of the chunk
+    const int qrow0 = warp * 16;                              // this warp's 16 query rows inside the tile
     uint32_t qf[HD / 16][4];
     float o[HD / 8][4];
 #pragma unroll
@@ -119,19 +115,18 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
 
     // one online-softmax pass of this warp's 16 query rows over the 64 keys j0.. held in (sK, sV)
     auto process_chunk = [&](int j0, const __half* sK, const __half* sV) {
-        if (j0 + kofs >= Nk) return;              // warp-uniform: this warp's keys of the chunk are all past the end
         const bool full = j0 + ATT_BN <= Nk;      // warp-uniform: no key of this chunk is masked
         // ---- S = Q K^T
-        float s[NG * 2][4];
+        float s[ATT_BN / 8][4];
 #pragma unroll
-        for (int i = 0; i < NG * 2; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+        for (int i = 0; i < ATT_BN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
 #pragma unroll
-        for (int np = 0; np < NG; ++np) {
-            if (j0 + kofs + np * 16 >= Nk) break;    // 16-key groups past the end are fully masked
+        for (int np = 0; np < ATT_BN / 16; ++np) {
+            if (j0 + np * 16 >= Nk) break;    // 16-key groups past the end are fully masked
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks) {
                 uint32_t kf[4];
-                ldmatrix_x4(kf, smem_u32(sK + (kofs + np * 16 + (lane & 7) + ((lane >> 4) << 3)) * LDS + ks * 16 + ((lane >> 3) & 1) * 8));
+                ldmatrix_x4(kf, smem_u32(sK + (np * 16 + (lane & 7) + ((lane >> 4) << 3)) * LDS + ks * 16 + ((lane >> 3) & 1) * 8));
                 mma_16816(s[2 * np], qf[ks], kf[0], kf[1]);
                 mma_16816(s[2 * np + 1], qf[ks], kf[2], kf[3]);
             }
@@ -141,13 +136,13 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
         float mx[2] = {NEG_BIG, NEG_BIG};
         if (full) {
 #pragma unroll
-            for (int nt = 0; nt < NG * 2; ++nt)
+            for (int nt = 0; nt < ATT_BN / 8; ++nt)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
         } else {
 #pragma unroll
-            for (int nt = 0; nt < NG * 2; ++nt) {
-                const int key = j0 + kofs + nt * 8 + 2 * t;
+            for (int nt = 0; nt < ATT_BN / 8; ++nt) {
+                const int key = j0 + nt * 8 + 2 * t;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     if (key + (e & 1) >= Nk) s[nt][e] = NEG_BIG;
@@ -166,8 +161,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
             msc[r] = -m_new;
         }
 #pragma unroll
-        for (int nt = 0; nt < NG * 2; ++nt) {
-            if (!full && j0 + kofs + (nt >> 1) * 16 >= Nk) break;      // same groups the MMAs skip
+        for (int nt = 0; nt < ATT_BN / 8; ++nt) {
+            if (!full && j0 + (nt >> 1) * 16 >= Nk) break;      // same groups the MMAs skip
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float pv = exp2f(fmaf(s[nt][e], p.scale_log2, msc[e >> 1]));
@@ -177,8 +172,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
         }
         if (weighted) {       // post-softmax, un-renormalised scaling of the last n_w key columns
 #pragma unroll
-            for (int nt = 0; nt < NG * 2; ++nt) {
-                const int key = j0 + kofs + nt * 8 + 2 * t;
+            for (int nt = 0; nt < ATT_BN / 8; ++nt) {
+                const int key = j0 + nt * 8 + 2 * t;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int kj = key + (e & 1);
@@ -199,8 +194,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
         }
         // ---- O += P V
 #pragma unroll
-        for (int kk = 0; kk < NG; ++kk) {
-            if (j0 + kofs + kk * 16 >= Nk) break;    // P is zero there
+        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+            if (j0 + kk * 16 >= Nk) break;    // P is zero there
             uint32_t a[4];
             a[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
             a[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
@@ -209,14 +204,14 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
 #pragma unroll
             for (int np = 0; np < HD / 16; ++np) {
                 uint32_t vf[4];
-                ldmatrix_x4_trans(vf, smem_u32(sV + (kofs + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8));
+                ldmatrix_x4_trans(vf, smem_u32(sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8));
                 mma_16816(o[2 * np], a, vf[0], vf[1]);
                 mma_16816(o[2 * np + 1], a, vf[2], vf[3]);
             }
         }
     };
 
-    const bool warp_active = KS == 4 || q0 + warp * 16 < p.P;   // warps past the last query only help with the loads
+    const bool warp_active = q0 + warp * 16 < p.P;       // warps past the last query only help with the loads
     int buf = 0;
     for (int j0 = 0; j0 < Nk; j0 += ATT_BN, buf ^= 1) {
         // prefetch the next chunk into the other buffer (all warps finished reading it at the end of the last iteration)
@@ -229,49 +224,16 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
         __syncthreads();                  // everyone is done with this buffer before it is refilled
     }
     cp_async_wait<0>();
-    if constexpr (KS == 1) {
-        // ---- normalise and store
+    // ---- normalise and store
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int row = q0 + warp * 16 + g + r * 8;
-            if (row < p.P) {
-                const float inv = 1.0f / l_run[r];
-                __half* dst = p.out + ((int64_t)b * p.P + row) * E + h * HD + 2 * t;
-#pragma unroll
-                for (int nt = 0; nt < HD / 8; ++nt)
-                    *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_half2(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
-            }
-        }
-    } else {
-        // ---- merge the four warps' partial results (the K buffers are dead after the loop's last barrier)
-        constexpr int LDP = HD + 2;           // fp32 partial O row + (max, sum)
-        float* part = reinterpret_cast<float*>(sKb);          // [4][16][LDP]  (4*16*LDP*4 <= 2*64*LDS*2 bytes)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            float* dst = part + (warp * 16 + g + r * 8) * LDP;
+    for (int r = 0; r < 2; ++r) {
+        const int row = q0 + warp * 16 + g + r * 8;
+        if (row < p.P) {
+            const float inv = 1.0f / l_run[r];
+            __half* dst = p.out + ((int64_t)b * p.P + row) * E + h * HD + 2 * t;
 #pragma unroll
             for (int nt = 0; nt < HD / 8; ++nt)
-                *reinterpret_cast<float2*>(dst + nt * 8 + 2 * t) = make_float2(o[nt][2 * r], o[nt][2 * r + 1]);
-            if (t == 0) { dst[HD] = m_run[r]; dst[HD + 1] = l_run[r]; }
-        }
-        __syncthreads();
-        for (int idx = tid; idx < 16 * (HD / 2); idx += 128) {
-            const int row = idx / (HD / 2), col = (idx - row * (HD / 2)) * 2;
-            if (q0 + row >= p.P) continue;
-            float mw[4], M = NEG_BIG;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) { mw[w] = part[(w * 16 + row) * LDP + HD]; M = fmaxf(M, mw[w]); }
-            float Lsum = 0.f, o0 = 0.f, o1 = 0.f;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const float* src = part + (w * 16 + row) * LDP;
-                const float f = exp2f(mw[w] - M);               // 0 for a warp that saw no key (max = -1e30)
-                Lsum = fmaf(src[HD + 1], f, Lsum);
-                o0 = fmaf(src[col], f, o0);
-                o1 = fmaf(src[col + 1], f, o1);
-            }
-            const float inv = 1.0f / Lsum;
-            *reinterpret_cast<uint32_t*>(p.out + ((int64_t)b * p.P + q0 + row) * E + h * HD + col) = pack_half2(o0 * inv, o1 * inv);
+                *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_half2(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
         }
     }
 }
@@ -283,9 +245,7 @@ int launch_attention(const AttnParams& p, cudaStream_t st) {
     if (p.B == 0 || p.P == 0) return 0;
     // algorithmic bytes: q, self k/v, out once; conditioning k/v once per sample
     ProfScope prof("attention", 2.0 * ((double)p.B * p.P * 4.0 * p.E + (double)p.B * p.S_max * 2.0 * p.E), st);
-    static const bool no_split = getenv("PB200_ATT_NOSPLIT") != nullptr;      // A/B knob
-    const bool split = !no_split && p.P <= 16;
-    dim3 grid(split ? 1 : ceil_div(p.P, ATT_BM), p.nhead, p.B);
+    dim3 grid(ceil_div(p.P, ATT_BM), p.nhead, p.B);
     PB_CHECK(grid.y <= 65535 && grid.z <= 65535, "attention: grid too large");
     const size_t smem = (size_t)(ATT_BM + 4 * ATT_BN) * (hd + 8) * sizeof(__half);
     switch (hd) {
@@ -293,12 +253,10 @@ int launch_attention(const AttnParams& p, cudaStream_t st) {
     case H: {                                                                                                       \
         static bool attr = false;                                                                                   \
         if (!attr) {                                                                                                \
-            PB_CUDA(cudaFuncSetAttribute(attention_kernel<H, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            PB_CUDA(cudaFuncSetAttribute(attention_kernel<H, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            PB_CUDA(cudaFuncSetAttribute(attention_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr = true;                                                                                            \
         }                                                                                                           \
-        if (split) attention_kernel<H, 4><<<grid, 128, smem, st>>>(p);                                              \
-        else attention_kernel<H, 1><<<grid, 128, smem, st>>>(p);                                                    \
+        attention_kernel<H><<<grid, 128, smem, st>>>(p);                                                            \
         break;                                                                                                      \
     }
         PB_ATT_CASE(16) PB_ATT_CASE(32) PB_ATT_CASE(64) PB_ATT_CASE(80) PB_ATT_CASE(96)

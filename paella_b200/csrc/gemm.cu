@@ -530,7 +530,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1)
 gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    const pb200_gemm_epilogue ep, int M, int N, int K) {
+                    const __grid_constant__ CUtensorMap tm_b_tail, const pb200_gemm_epilogue ep, int M, int N, int K,
+                    int n_main, int tail_bn) {
     constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
     constexpr int BH_BYTES = (BLOCK_N / 2) * GEMM_BLOCK_K * 2;       // this CTA's half of the W tile
     constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
@@ -553,8 +554,30 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const bool leader = crank == 0;
     const int n_tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
     const int n_pairs_m = (M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
-    const int n_units = n_pairs_m * n_tiles_n;
+    // Work units.  Units [0, n_main) are full 256 x BLOCK_N pair tiles.  With a tail (tail_bn > 0) the remaining pair
+    // tiles -- the ones that would form a mostly idle last wave -- are cut into BLOCK_N / tail_bn narrower tiles of
+    // tail_bn columns, so the last wave is short and (nearly) full instead (8192 x 1280: 160 tiles on 74 SM pairs =
+    // 2.16 waves ran as 3; with the 12 leftover tiles split 4 ways it runs as 2 + a quarter-width wave).
+    const int n_big = n_pairs_m * n_tiles_n;
+    const int tail_split = tail_bn > 0 ? BLOCK_N / tail_bn : 1;
+    const int n_units = tail_bn > 0 ? n_main + (n_big - n_main) * tail_split : n_big;
     const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
+    struct Unit { int m_pair, n0, width; };
+    auto decode = [&](int u) {
+        Unit r;
+        int big = u, sub = 0;
+        r.width = BLOCK_N;
+        if (u >= n_main && tail_bn > 0) {
+            const int v = u - n_main;
+            big = n_main + v / tail_split;
+            sub = v - (v / tail_split) * tail_split;
+            r.width = tail_bn;
+        }
+        r.m_pair = big / n_tiles_n;
+        r.n0 = (big - r.m_pair * n_tiles_n) * BLOCK_N + sub * r.width;
+        if (r.n0 >= N) r.width = 0;           // a sub-tile entirely past the last column: every role skips it
+        return r;
+    };
     const int n_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
 
     if (warp == 0 && lane == 0) {
@@ -590,16 +613,20 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             uint32_t phase = 0;
             const uint32_t leader_full0 = ptx::mapa(full_bar(0), 0);      // leader's full[0] in cluster address space
             for (int unit = unit0; unit < n_units; unit += unit_step) {
-                const int m_idx = (unit / n_tiles_n) * (2 * GEMM_BLOCK_M) + (int)crank * GEMM_BLOCK_M;
-                const int n_idx = (unit % n_tiles_n) * BLOCK_N + (int)crank * (BLOCK_N / 2);
+                const Unit un = decode(unit);
+                if (un.width == 0) continue;
+                const int m_idx = un.m_pair * (2 * GEMM_BLOCK_M) + (int)crank * GEMM_BLOCK_M;
+                const int n_idx = un.n0 + (int)crank * (un.width / 2);
+                const bool narrow = un.width != BLOCK_N;
+                const uint32_t tx = 2u * (uint32_t)(A_BYTES + (un.width / 2) * GEMM_BLOCK_K * 2);
                 for (int kb = 0; kb < n_kb; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t lfull = leader_full0 + 8u * stage;
-                    if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+                    if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), tx);
                     else ptx::mbar_arrive_cluster(lfull);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     ptx::tma_load_2d_cg2(&tm_a, lfull, sa, kb * GEMM_BLOCK_K, m_idx);
-                    ptx::tma_load_2d_cg2(&tm_b, lfull, sa + A_BYTES, kb * GEMM_BLOCK_K, n_idx);
+                    ptx::tma_load_2d_cg2(narrow ? &tm_b_tail : &tm_b, lfull, sa + A_BYTES, kb * GEMM_BLOCK_K, n_idx);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -607,11 +634,15 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader) {
-            constexpr uint32_t idesc = ptx::umma_idesc_f16(2 * GEMM_BLOCK_M, BLOCK_N, 0);
+            constexpr uint32_t idesc_full = ptx::umma_idesc_f16(2 * GEMM_BLOCK_M, BLOCK_N, 0);
+            const uint32_t idesc_tail = ptx::umma_idesc_f16(2 * GEMM_BLOCK_M, tail_bn > 0 ? tail_bn : BLOCK_N, 0);
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            for (int unit = unit0; unit < n_units; unit += unit_step, ++iter) {
+            for (int unit = unit0; unit < n_units; unit += unit_step) {
+                const Unit un = decode(unit);
+                if (un.width == 0) continue;
+                const uint32_t idesc = un.width == BLOCK_N ? idesc_full : idesc_tail;
                 const int as = iter & 1;
                 const uint32_t aphase = (iter >> 1) & 1;
                 ptx::mbar_wait(tempty_bar(as), aphase ^ 1);
@@ -633,6 +664,7 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                ++iter;
             }
         }
     } else {
@@ -642,18 +674,23 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         constexpr int COLS_PER_WARP = BLOCK_N / (EW / 4);
         const uint32_t leader_tempty0 = ptx::mapa(tempty_bar(0), 0);
         int iter = 0;
-        for (int unit = unit0; unit < n_units; unit += unit_step, ++iter) {
+        for (int unit = unit0; unit < n_units; unit += unit_step) {
+            const Unit un = decode(unit);
+            if (un.width == 0) continue;
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
-            const int m_idx = (unit / n_tiles_n) * (2 * GEMM_BLOCK_M) + (int)crank * GEMM_BLOCK_M;
-            const int n_idx = (unit % n_tiles_n) * BLOCK_N;
+            ++iter;
+            const int m_idx = un.m_pair * (2 * GEMM_BLOCK_M) + (int)crank * GEMM_BLOCK_M;
+            const int n_idx = un.n0;
             const int row = m_idx + q * 32 + lane;
+            const int c_end = min((slice + 1) * COLS_PER_WARP, un.width);      // a narrow tile leaves the upper slices idle
             EpiPre<MODE> pre;
-            if (n_idx + slice * COLS_PER_WARP < N) epilogue_preload<MODE>(ep, M, N, row, n_idx + slice * COLS_PER_WARP, pre, lane);
+            if (slice * COLS_PER_WARP < c_end && n_idx + slice * COLS_PER_WARP < N)
+                epilogue_preload<MODE>(ep, M, N, row, n_idx + slice * COLS_PER_WARP, pre, lane);
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
 #pragma unroll 1
-            for (int c = slice * COLS_PER_WARP; c < (slice + 1) * COLS_PER_WARP; c += 32) {
+            for (int c = slice * COLS_PER_WARP; c < c_end; c += 32) {
                 if (n_idx + c >= N) break;
                 if (c != slice * COLS_PER_WARP) epilogue_preload<MODE>(ep, M, N, row, n_idx + c, pre, lane);
                 float v[32];
@@ -672,8 +709,8 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 }
 
 template <int BLOCK_N, int MODE>
-static int launch_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_gemm_epilogue& ep, int M, int N, int K,
-                      cudaStream_t st) {
+static int launch_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tb_tail, int tail_bn,
+                      const pb200_gemm_epilogue& ep, int M, int N, int K, cudaStream_t st) {
     constexpr int STAGES = BLOCK_N >= 256 ? 6 : 8;
     constexpr int SMEM = STAGES * (GEMM_BLOCK_M * 128 + (BLOCK_N / 2) * 128) + 1024 + 256;
     static bool attr_set = false;
@@ -681,8 +718,11 @@ static int launch_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_
         PB_CUDA(cudaFuncSetAttribute(gemm_f16_cg2_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
-    const int n_units = ceil_div(M, 2 * GEMM_BLOCK_M) * ceil_div(N, BLOCK_N);
+    const int n_big = ceil_div(M, 2 * GEMM_BLOCK_M) * ceil_div(N, BLOCK_N);
     const int max_pairs = sm_count() / 2;
+    if (!tb_tail || tail_bn <= 0 || tail_bn >= BLOCK_N || BLOCK_N % tail_bn != 0) { tail_bn = 0; tb_tail = &tb; }
+    const int n_main = tail_bn ? (n_big / max_pairs) * max_pairs : n_big;      // the complete waves
+    const int n_units = n_main + (n_big - n_main) * (tail_bn ? BLOCK_N / tail_bn : 1);
     const int grid = 2 * (n_units < max_pairs ? n_units : max_pairs);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -697,21 +737,21 @@ static int launch_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_cg2_kernel<BLOCK_N, MODE>, ta, tb, ep, M, N, K));
+    PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_cg2_kernel<BLOCK_N, MODE>, ta, tb, *tb_tail, ep, M, N, K, n_main, tail_bn));
     PB_LAUNCH_CHECK();
     return 0;
 }
 
 template <int BLOCK_N>
-static int launch_cg2_mode(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_gemm_epilogue& ep, int M, int N, int K,
-                           cudaStream_t st) {
+static int launch_cg2_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tb_tail, int tail_bn,
+                           const pb200_gemm_epilogue& ep, int M, int N, int K, cudaStream_t st) {
     switch (ep.mode) {
-        case PB200_EPI_F16: return launch_cg2<BLOCK_N, PB200_EPI_F16>(ta, tb, ep, M, N, K, st);
-        case PB200_EPI_F32: return launch_cg2<BLOCK_N, PB200_EPI_F32>(ta, tb, ep, M, N, K, st);
-        case PB200_EPI_GELU_F16: return launch_cg2<BLOCK_N, PB200_EPI_GELU_F16>(ta, tb, ep, M, N, K, st);
-        case PB200_EPI_RESID_F32: return launch_cg2<BLOCK_N, PB200_EPI_RESID_F32>(ta, tb, ep, M, N, K, st);
-        case PB200_EPI_UNPATCH_F32: return launch_cg2<BLOCK_N, PB200_EPI_UNPATCH_F32>(ta, tb, ep, M, N, K, st);
-        case PB200_EPI_NCHW_F32: return launch_cg2<BLOCK_N, PB200_EPI_NCHW_F32>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_F16: return launch_cg2<BLOCK_N, PB200_EPI_F16>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
+        case PB200_EPI_F32: return launch_cg2<BLOCK_N, PB200_EPI_F32>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
+        case PB200_EPI_GELU_F16: return launch_cg2<BLOCK_N, PB200_EPI_GELU_F16>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
+        case PB200_EPI_RESID_F32: return launch_cg2<BLOCK_N, PB200_EPI_RESID_F32>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
+        case PB200_EPI_UNPATCH_F32: return launch_cg2<BLOCK_N, PB200_EPI_UNPATCH_F32>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
+        case PB200_EPI_NCHW_F32: return launch_cg2<BLOCK_N, PB200_EPI_NCHW_F32>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
     }
     PB_CHECK(false, "gemm: unknown epilogue mode %d", ep.mode);
     return 1;
@@ -835,8 +875,31 @@ int gemm_pick_block_n(int64_t M, int64_t N, int64_t K, bool allow_cg2) {
     return best;
 }
 
+int gemm_tail_block_n(int64_t M, int64_t N, int block_n) {
+    // Worth it when the leftover tiles are a small part of a wave: cut them so that the last wave is full but narrow.
+    // A narrow tile costs more per column than a full one (A is re-read per tile: the L2->SM fabric model of
+    // gemm_pick_block_n), hence the 0.55 / 0.45 weights; measured on 8192 x 1280 x {1280, 5120}.
+    static const int force = getenv("PB200_GEMM_TAIL") ? atoi(getenv("PB200_GEMM_TAIL")) : -1;   // 0 disables, 64/128 force
+    if (!gemm_use_cg2(M) || block_n != 256) return 0;
+    const long workers = sm_count() / 2;
+    const long n_big = (long)ceil_div(M, 2 * GEMM_BLOCK_M) * ceil_div(N, block_n);
+    const long rem = n_big % workers;
+    if (n_big < workers || rem == 0) return 0;
+    if (force >= 0) return (force == 64 || force == 128) ? force : 0;
+    double best = 1.0;                 // cost of running the leftover as one more full wave
+    int pick = 0;
+    const int cand[2] = {128, 64};
+    const double weight[2] = {0.55, 0.45};
+    for (int i = 0; i < 2; ++i) {
+        const long sub = rem * (block_n / cand[i]);
+        const double cost = (double)((sub + workers - 1) / workers) * weight[i];
+        if (cost < best - 0.15) { best = cost; pick = cand[i]; }
+    }
+    return pick;
+}
+
 int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const pb200_gemm_epilogue& ep, int64_t M,
-                int64_t N, int64_t K, cudaStream_t st) {
+                int64_t N, int64_t K, cudaStream_t st, const GemmTail* tail) {
     PB_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem");
     PB_CHECK(N % 8 == 0, "gemm: N=%lld must be a multiple of 8", (long long)N);
     PB_CHECK(ep.out != nullptr, "gemm: null output");
@@ -850,8 +913,10 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const
     static const char* kTags[6] = {"gemm_f16", "gemm_f32", "gemm_gelu_sqsum", "gemm_resid", "gemm_unpatch", "gemm_nchw"};
     ProfScope prof(ep.mode >= 0 && ep.mode < 6 ? kTags[ep.mode] : "gemm", 2.0 * (double)M * (double)N * (double)K, st);
     if (gemm_use_cg2(M) && block_n >= 128) {
-        if (block_n == 256) return launch_cg2_mode<256>(ta, tb, ep, (int)M, (int)N, (int)K, st);
-        return launch_cg2_mode<128>(ta, tb, ep, (int)M, (int)N, (int)K, st);
+        const int tbn = tail ? tail->bn : 0;
+        const CUtensorMap* ttb = tail ? tail->tb : nullptr;
+        if (block_n == 256) return launch_cg2_mode<256>(ta, tb, ttb, tbn, ep, (int)M, (int)N, (int)K, st);
+        return launch_cg2_mode<128>(ta, tb, ttb, tbn, ep, (int)M, (int)N, (int)K, st);
     }
     switch (block_n) {
         case 64: return launch_mode<64>(ta, tb, ep, (int)M, (int)N, (int)K, st);
@@ -866,10 +931,12 @@ int gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, 
              const pb200_gemm_epilogue& ep, cudaStream_t st) {
     PB_CHECK(K % 8 == 0, "gemm: K=%lld must be a multiple of 8", (long long)K);
     const int bn = gemm_pick_block_n(M, N, K);
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tbt;
     PB_TRY(make_tmap_f16_2d(&ta, a, M, K, lda, GEMM_BLOCK_M));
     PB_TRY(make_tmap_f16_2d(&tb, w, N, K, ldw, bn / 2));      // W box = half a tile (see the producer)
-    return gemm_launch(ta, tb, bn, ep, M, N, K, st);
+    GemmTail tail{gemm_tail_block_n(M, N, bn), &tbt};
+    if (tail.bn) PB_TRY(make_tmap_f16_2d(&tbt, w, N, K, ldw, tail.bn / 2));
+    return gemm_launch(ta, tb, bn, ep, M, N, K, st, tail.bn ? &tail : nullptr);
 }
 
 }  // namespace pb

@@ -50,8 +50,16 @@ int gemm_conv_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, 
 // conv (TMA-gather) variants, which run on the 1-SM kernel
 int gemm_pick_block_n(int64_t M, int64_t N, int64_t K = 0, bool allow_cg2 = true);
 
+// Narrow tiles for the leftover of the last wave (2-SM kernel, BLOCK_N 256): 0 = none, else 64 or 128; tb = tensor map of
+// W with box rows bn / 2.
+struct GemmTail {
+    int bn;
+    const CUtensorMap* tb;
+};
+int gemm_tail_block_n(int64_t M, int64_t N, int block_n);
+
 int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const pb200_gemm_epilogue& ep, int64_t M,
-                int64_t N, int64_t K, cudaStream_t st);
+                int64_t N, int64_t K, cudaStream_t st, const GemmTail* tail = nullptr);
 
 // convenience: builds both tensor maps and launches
 int gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int64_t N, int64_t K,

@@ -147,7 +147,9 @@ struct pb200_paella {
         const CUtensorMap *ta, *tb;
         PB_TRY(tmap(A, M, K, lda, GEMM_BLOCK_M, &ta));
         PB_TRY(tmap(w<__half>(w_off), N, K, K, bn / 2, &tb));     // W box = half a tile
-        return gemm_launch(*ta, *tb, bn, ep, M, N, K, st);
+        GemmTail tail{gemm_tail_block_n(M, N, bn), nullptr};
+        if (tail.bn) PB_TRY(tmap(w<__half>(w_off), N, K, K, tail.bn / 2, &tail.tb));
+        return gemm_launch(*ta, *tb, bn, ep, M, N, K, st, tail.bn ? &tail : nullptr);
     }
 };
 
