@@ -226,11 +226,15 @@ int pb200_paella_c_embeddings(pb200_paella* m, const pb200_cond* cond, int batch
  * features fp32 [Bt*H*W, c_out] (rows (b,y,x)).  attn_weights fp32 [n_attn_weights] or NULL scales
  * the last n key columns after the softmax for samples [0, attn_weights_batch)
  * (ref/utils/alter_attention.py:23-34; the notebook passes it on the conditional forward only).
+ * cond_cache was prepared for cache_slots sample slots (the batch_total of pb200_paella_prepare_cond); kv_slot int32
+ * [batch_total] names the slot each sample attends to (NULL: slot i for sample i, cache_slots == batch_total) -- samples
+ * with identical conditioning, e.g. the unconditional half of a CFG batch, share one slot and its K/V is read once.
  * cfg_pairs = 1: the classifier-free-guidance batch of ref/src/utils.py:42-45 -- tokens [Bt/2,H,W] and r [Bt/2] are
  * given once, sample i + Bt/2 is sample i under the unconditional rows of the conditioning cache.  The blocks before
  * the first AttnBlock do not see the conditioning and are evaluated once per pair (identical arithmetic). */
 int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r, int batch_total, int cfg_pairs, int h, int w,
-                          const void* cond_cache, int s_max, const float* attn_weights, int n_attn_weights,
+                          const void* cond_cache, int cache_slots, const int* kv_slot, int s_max, const float* attn_weights,
+                          int n_attn_weights,
                           int attn_weights_batch, float* features, void* workspace, int64_t workspace_bytes,
                           void* stream);
 

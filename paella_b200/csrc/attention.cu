@@ -60,10 +60,11 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     const int E = p.E;
     const int64_t ldq = 3 * (int64_t)E, ldc = 2 * (int64_t)E;
     const int n_self = p.self_attn ? p.P : 0;
-    const int n_cond = p.kv_len ? p.kv_len[b] : p.S_max;
+    const int slot = p.kv_slot ? p.kv_slot[b] : b;            // samples with identical conditioning share one K/V block
+    const int n_cond = p.kv_len ? p.kv_len[slot] : p.S_max;
     const int Nk = n_self + n_cond;
     const __half* qkv_b = p.qkv + (int64_t)b * p.P * ldq;
-    const __half* ckv_b = p.ckv + (int64_t)b * p.S_max * ldc;
+    const __half* ckv_b = p.ckv + (int64_t)slot * p.S_max * ldc;
 
     // K/V chunk j0.. -> buffer `buf` with 16-byte cp.async (zero-fill for keys past the end)
     auto load_chunk = [&](int j0, int buf) {

@@ -7,7 +7,8 @@ namespace pb {
 struct AttnParams {
     const __half* qkv;     // [B*P, 3E]: q | k_self | v_self
     const __half* ckv;     // [B, S_max, 2E]: k_cond | v_cond
-    const int* kv_len;     // [B] valid conditioning rows per sample (NULL: S_max)
+    const int* kv_len;     // [slots] valid conditioning rows per cache slot (NULL: S_max)
+    const int* kv_slot;    // [B] cache slot (sample block of ckv / entry of kv_len) each sample reads; NULL: slot = sample
     __half* out;           // [B*P, E]
     int B, P, S_max, E, nhead;
     int self_attn;         // keys = [self ; cond] (1) or cond only (0)

@@ -148,6 +148,7 @@ int pb200_attention(const void* qkv16, const void* ckv16, const int* kv_len, voi
     p.qkv = reinterpret_cast<const __half*>(qkv16);
     p.ckv = reinterpret_cast<const __half*>(ckv16 ? ckv16 : qkv16);
     p.kv_len = kv_len;
+    p.kv_slot = nullptr;
     p.out = reinterpret_cast<__half*>(out16);
     p.B = batch; p.P = positions; p.S_max = s_max; p.E = embed; p.nhead = nhead;
     p.self_attn = self_attn;

@@ -534,7 +534,8 @@ int pb200_paella_prepare_cond(pb200_paella* m, const pb200_cond* cond, int batch
 }
 
 int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r, int batch_total, int cfg_pairs, int h, int w,
-                          const void* cond_cache, int s_max, const float* attn_weights, int n_attn_weights,
+                          const void* cond_cache, int cache_slots, const int* kv_slot, int s_max, const float* attn_weights,
+                          int n_attn_weights,
                           int attn_weights_batch, float* features, void* workspace, int64_t workspace_bytes,
                           void* stream) {
     PB_CHECK(m->blob != nullptr, "features: weights not bound");
@@ -549,7 +550,9 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
     plan_features(m, Bt, h, w, ar, ws);
     PB_CHECK(ar.off <= workspace_bytes, "features: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)ar.off);
     const uint8_t* cache = reinterpret_cast<const uint8_t*>(cond_cache);
-    const int* kv_len = reinterpret_cast<const int*>(cache + cond_block_off(m, m->n_attn, Bt, s_max));
+    PB_CHECK(cache_slots > 0 && (kv_slot != nullptr || cache_slots == Bt), "features: %d cache slots for %d samples need a slot map",
+             cache_slots, Bt);
+    const int* kv_len = reinterpret_cast<const int*>(cache + cond_block_off(m, m->n_attn, cache_slots, s_max));
 
     int gh[PB200_MAX_LEVELS], gw[PB200_MAX_LEVELS];
     for (int l = 0; l < L; ++l) { gh[l] = (h / ps) >> l; gw[l] = (w / ps) >> l; }
@@ -649,8 +652,9 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
                 PB_TRY(m->gemm(ws.a16, ch, M, ch, b.inproj_w, 3 * (int64_t)ch, e1, st));
                 AttnParams ap;
                 ap.qkv = ws.qkv16;
-                ap.ckv = reinterpret_cast<const __half*>(cache + cond_block_off(m, b.attn_index, Bt, s_max));
+                ap.ckv = reinterpret_cast<const __half*>(cache + cond_block_off(m, b.attn_index, cache_slots, s_max));
                 ap.kv_len = kv_len;
+                ap.kv_slot = kv_slot;
                 ap.out = ws.o16;
                 ap.B = Bt; ap.P = P; ap.S_max = s_max; ap.E = ch; ap.nhead = c.nhead[l];
                 ap.self_attn = c.self_attn;

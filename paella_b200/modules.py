@@ -261,8 +261,13 @@ class ConditioningCache:
     """x- and t-independent conditioning work of one sample() call: c_embed and every AttnBlock's
     cond K/V for ``batch_total`` samples (conditional rows first, then unconditional rows)."""
 
-    def __init__(self, cache: torch.Tensor, batch_total: int, s_max: int):
+    def __init__(self, cache: torch.Tensor, batch_total: int, s_max: int, slots: Optional[int] = None,
+                 slot_map: Optional[torch.Tensor] = None):
         self.cache, self.batch_total, self.s_max = cache, batch_total, s_max
+        # a group whose samples all carry the same conditioning (the unconditional half of a CFG batch) occupies ONE
+        # slot of the cache; slot_map (int32 [batch_total], None = identity) names the slot each sample attends to
+        self.slots = batch_total if slots is None else slots
+        self.slot_map = slot_map
 
 
 class Paella(nn.Module):
@@ -431,9 +436,11 @@ class Paella(nn.Module):
         return self._workspace
 
     # -------------------------------------------------------------- conditioning
-    def prepare_conditioning(self, groups: Sequence[Dict[str, torch.Tensor]], latent_hw=(32, 32)) -> ConditioningCache:
+    def prepare_conditioning(self, groups: Sequence[Dict[str, torch.Tensor]], latent_hw=(32, 32),
+                             share_uniform: bool = True) -> ConditioningCache:
         """gen_c_embeddings (ref/src/modules.py:223-232) + every AttnBlock's kv_mapper and K/V projection of the
-        conditioning rows, for the concatenation of ``groups`` (e.g. [conditional, unconditional])."""
+        conditioning rows, for the concatenation of ``groups`` (e.g. [conditional, unconditional]).  A group whose
+        samples all carry the same tensors (the usual unconditional group) is projected once and shared."""
         self._ensure_packed()
         L = lib()
         dev = self._device()
@@ -447,12 +454,32 @@ class Paella(nn.Module):
             return g["byt5"].shape[1] + seq * n
         s_max = max(seqlen(g) for g in groups)
         bt = sum(g["byt5"].shape[0] for g in groups)
+
+        def uniform(g):
+            """All samples of the group carry identical conditioning (one host sync per tensor, once per sample() call)."""
+            if not share_uniform or g["byt5"].shape[0] < 2:
+                return False
+            ts = [g["byt5"], g.get("clip")]
+            ci = g.get("clip_image")
+            ts += list(ci) if isinstance(ci, (list, tuple)) else [ci]
+            return all(bool((t == t[:1]).all()) for t in ts if t is not None)
+        shared = [uniform(g) for g in groups]
+        slots = sum(1 if sh else g["byt5"].shape[0] for g, sh in zip(groups, shared))
         with torch.cuda.device(dev):
-            cache = torch.empty(L.pb200_paella_cond_cache_bytes(self._handle, bt, s_max), dtype=torch.uint8, device=dev)
+            cache = torch.empty(L.pb200_paella_cond_cache_bytes(self._handle, slots, s_max), dtype=torch.uint8, device=dev)
             ws = self._ws(L.pb200_paella_workspace_bytes(self._handle, bt, latent_hw[0], latent_hw[1], s_max))
             off = 0
             keep = []
-            for g in groups:
+            slot_of = []
+            for g, sh in zip(groups, shared):
+                n_g = g["byt5"].shape[0]
+                if sh:
+                    ci = g.get("clip_image")
+                    g = {"byt5": g["byt5"][:1], "clip": g["clip"][:1] if g.get("clip") is not None else None,
+                         "clip_image": ([t[:1] for t in ci] if isinstance(ci, (list, tuple)) else ci[:1]) if ci is not None else None}
+                    slot_of += [off] * n_g
+                else:
+                    slot_of += list(range(off, off + n_g))
                 byt5 = g["byt5"].to(device=dev, dtype=torch.float32).contiguous()
                 B = byt5.shape[0]
                 cond = _lib.Cond()
@@ -468,10 +495,11 @@ class Paella(nn.Module):
                     ci = ci.contiguous()
                     cond.clip_image, cond.n_clip_image = ptr(ci).value, ci.shape[0]
                 keep += [byt5, clip, ci]
-                check(L.pb200_paella_prepare_cond(self._handle, ctypes.byref(cond), B, off, bt, s_max, ptr(cache), ptr(ws),
+                check(L.pb200_paella_prepare_cond(self._handle, ctypes.byref(cond), B, off, slots, s_max, ptr(cache), ptr(ws),
                                                   ws.numel(), current_stream()), "pb200_paella_prepare_cond")
                 off += B
-        return ConditioningCache(cache, bt, s_max)
+            slot_map = torch.tensor(slot_of, dtype=torch.int32, device=dev) if slots != bt else None
+        return ConditioningCache(cache, bt, s_max, slots, slot_map)
 
     def gen_r_embedding(self, r, max_positions=10000):
         """ref/src/modules.py:212-221 -> [B, c_r]."""
@@ -535,7 +563,8 @@ class Paella(nn.Module):
             ws = self._ws(L.pb200_paella_workspace_bytes(self._handle, Bt, H, W, cond.s_max))
             feats = torch.empty(Bt * H * W, self._cfg["c_out"], dtype=torch.float32, device=dev)
             aw = attn_weights.to(device=dev, dtype=torch.float32).contiguous() if attn_weights is not None else None
-            check(L.pb200_paella_features(self._handle, ptr(x), ptr(r), Bt, int(cfg_pairs), H, W, ptr(cond.cache), cond.s_max, ptr(aw),
+            check(L.pb200_paella_features(self._handle, ptr(x), ptr(r), Bt, int(cfg_pairs), H, W, ptr(cond.cache), cond.slots,
+                                          ptr(cond.slot_map), cond.s_max, ptr(aw),
                                           aw.numel() if aw is not None else 0, attn_weights_batch, ptr(feats), ptr(ws),
                                           ws.numel(), current_stream()), "pb200_paella_features")
         return feats

@@ -251,6 +251,28 @@ def test_cfg_pairs_prefix_sharing_is_exact(which, tiny, default_model):
     assert not torch.equal(full[: full.shape[0] // 2], full[full.shape[0] // 2:])       # the two halves do differ
 
 
+@pytest.mark.parametrize("which", ["tiny", "default"])
+def test_shared_conditioning_slot_matches_per_sample_cache(which, tiny, default_model):
+    """An unconditional group with identical rows is projected once and shared through the slot map: same features as
+    the cache that stores every sample's K/V (the K/V GEMM runs on 1 x S instead of B x S rows; same per-element sums)."""
+    from paella_b200.synth import synthetic_conditioning
+    m = tiny[0] if which == "tiny" else default_model[0]
+    B, L = 3, 16
+    kw = dict(byt5_embd=m.byt5_mapper.in_features, clip_embd=m.clip_mapper.in_features)
+    cond, uncond = synthetic_conditioning(B, L, device=DEV, **kw)
+    shared = m.prepare_conditioning([cond, uncond], (16, 16))
+    plain = m.prepare_conditioning([cond, uncond], (16, 16), share_uniform=False)
+    assert shared.slots == B + 1 and shared.slot_map.tolist() == [0, 1, 2, 3, 3, 3]
+    assert plain.slots == 2 * B and plain.slot_map is None
+    x = torch.randint(0, m.num_labels, (B, 16, 16), device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    r = torch.tensor([0.8, 0.4, 0.2], device=DEV)
+    a = m.features(x, r, shared, cfg_pairs=True)
+    b = m.features(x, r, plain, cfg_pairs=True)
+    mx, rms = _errs(a, b)
+    _log("shared_cond_slot", {"which": which, "max_abs": mx, "rms": rms, "equal": bool(torch.equal(a, b))})
+    assert mx < 1e-5
+
+
 def test_notebook_sampler_modes_and_intermediates(tiny):
     """paella_inference.ipynb cell-3 signature: modes multinomial / argmax / quant, sampling_quant_steps, attn_weights,
     init_x, sampling_conditional_steps; returns (sampled, intermediates) with one entry per resample and per renoise."""
