@@ -428,61 +428,6 @@ int launch_dwconv_ln(const float* x, const float* skip, const float* w_packed, c
 }
 
 // ------------------------------------------------------------------ GlobalResponseNorm
-__global__ void __launch_bounds__(256) grn_scale_kernel(float* __restrict__ sqsum, const float* __restrict__ gamma, int N,
-                                                        float* __restrict__ scale) {
-    const int b = blockIdx.x;
-    float* sq = sqsum + (int64_t)b * N;
-    float s = 0.f;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s += sqrtf(sq[i]);
-    __shared__ float red[8];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    float tot = 0.f;
-    for (int i = 0; i < 8; ++i) tot += red[i];
-    const float denom = tot / N + 1e-6f;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const float gx = sqrtf(sq[i]);
-        scale[(int64_t)b * N + i] = fmaf(gamma[i], gx / denom, 1.0f);
-        sq[i] = 0.f;          // ready for the next ResBlock's GEMM epilogue
-    }
-}
-
-__global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ h, int64_t M, int N, int P,
-                                                        const float* __restrict__ scale, const float* __restrict__ beta) {
-    const int nv = N >> 3;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M * nv) return;
-    const int64_t row = i / nv;
-    const int col = (int)(i - row * nv) * 8;
-    const float* sc = scale + (row / P) * N + col;
-    uint4 v = *reinterpret_cast<uint4*>(h + row * N + col);
-    __half2* hv = reinterpret_cast<__half2*>(&v);
-    const float4 s0 = *reinterpret_cast<const float4*>(sc), s1 = *reinterpret_cast<const float4*>(sc + 4);
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
-    float2 f;
-    f = __half22float2(hv[0]); hv[0] = __floats2half2_rn(fmaf(f.x, s0.x, b0.x), fmaf(f.y, s0.y, b0.y));
-    f = __half22float2(hv[1]); hv[1] = __floats2half2_rn(fmaf(f.x, s0.z, b0.z), fmaf(f.y, s0.w, b0.w));
-    f = __half22float2(hv[2]); hv[2] = __floats2half2_rn(fmaf(f.x, s1.x, b1.x), fmaf(f.y, s1.y, b1.y));
-    f = __half22float2(hv[3]); hv[3] = __floats2half2_rn(fmaf(f.x, s1.z, b1.z), fmaf(f.y, s1.w, b1.w));
-    *reinterpret_cast<uint4*>(h + row * N + col) = v;
-}
-
-int launch_grn_scale(float* sqsum, const float* gamma, int B, int N, float* scale, cudaStream_t st) {
-    ProfScope prof("grn", (double)B * N * 12.0, st);
-    grn_scale_kernel<<<B, 256, 0, st>>>(sqsum, gamma, N, scale);
-    PB_LAUNCH_CHECK();
-    return 0;
-}
-
-int launch_grn_apply(__half* h, int64_t M, int N, int P, const float* scale, const float* beta, cudaStream_t st) {
-    ProfScope prof("grn", (double)M * N * 4.0, st);
-    PB_CHECK(N % 8 == 0, "grn: N=%d must be a multiple of 8", N);
-    grn_apply_kernel<<<ceil_div(M * (N / 8), 256), 256, 0, st>>>(h, M, N, P, scale, beta);
-    PB_LAUNCH_CHECK();
-    return 0;
-}
-
 // One-kernel GRN: every CTA recomputes its sample's normaliser mean_n sqrt(sq[b,n]) (N fp32 values from L2), then
 // rescales its rows.  sq_next (the other half of a ping-pong pair) is zeroed for the next block's GEMM epilogue,
 // so the statistic buffer being read is never written in the same launch.

@@ -22,12 +22,7 @@ int launch_ln_patchify2(const float* x, int B, int h, int w, int c, __half* out,
 int launch_dwconv_ln(const float* x, const float* skip, const float* w_packed, const float* bias, int B, int h, int w,
                      int c, int k, __half* out, cudaStream_t st);
 
-// GlobalResponseNorm: scale[b,n] = 1 + gamma[n]*Gx/(mean_n Gx + 1e-6), Gx = sqrt(sqsum[b,n]); zeroes sqsum afterwards
-int launch_grn_scale(float* sqsum, const float* gamma, int B, int N, float* scale, cudaStream_t st);
-// h[m,n] = h*scale[m/P,n] + beta[n] in place (fp16)
-int launch_grn_apply(__half* h, int64_t M, int N, int P, const float* scale, const float* beta, cudaStream_t st);
-
-// both of the above in one launch: h[b,p,n] = h*(1 + gamma[n]*Gx[b,n]/(mean_n Gx + 1e-6)) + beta[n], Gx = sqrt(sq[b,n]);
+// GlobalResponseNorm in one launch: h[b,p,n] = h*(1 + gamma[n]*Gx[b,n]/(mean_n Gx + 1e-6)) + beta[n], Gx = sqrt(sq[b,n]);
 // zeroes all B*zero_per_sample floats of sq_next (the other buffer of a ping-pong pair) for the next block
 int launch_grn_fused(__half* h, int B, int P, int N, const uint64_t* sq, uint64_t* sq_next, int zero_per_sample, const float* gamma,
                      const float* beta, cudaStream_t st);
