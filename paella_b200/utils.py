@@ -78,6 +78,24 @@ def _sample_core(model: Paella, model_inputs, latent_shape, unconditional_inputs
     return sampled, intermediates
 
 
+def load_conditional_models(byt5_model_name, vqgan_path, device):
+    """ref/src/utils.py:24-32: the f4 codec from ``vqgan_path`` (a ``{'state_dict': ...}`` checkpoint, as saved by the
+    reference's training code) and the ByT5 text encoder.  The codec is this package's VQModel; the text encoder is
+    the third-party ``transformers`` model exactly as in the reference (outside the hot path) —
+    ``byt5_model_name=None`` skips it."""
+    from .vqgan import VQModel
+    vqgan = VQModel().to(device)
+    ckpt = torch.load(vqgan_path, map_location=device)
+    vqgan.load_state_dict(ckpt["state_dict"] if isinstance(ckpt, dict) and "state_dict" in ckpt else ckpt)
+    vqgan.eval().requires_grad_(False)
+    if byt5_model_name is None:
+        return vqgan, None
+    from transformers import AutoTokenizer, T5EncoderModel
+    byt5 = T5EncoderModel.from_pretrained(byt5_model_name).to(device).eval().requires_grad_(False)
+    byt5_tokenizer = AutoTokenizer.from_pretrained(byt5_model_name)
+    return vqgan, (byt5_tokenizer, byt5)
+
+
 def sample(model, model_inputs, latent_shape, unconditional_inputs=None, steps=12, renoise_steps=11, temperature=(1.0, 0.2),
            cfg=8.0, t_start=1.0, t_end=0.0, device="cuda", exact=False):
     """ref/src/utils.py:35-55 (same positional/keyword arguments; ``device`` is accepted and must be the model's).

@@ -1,2 +1,2 @@
 """Import-path shim for the reference's ``src/utils.py``: ``sample`` with the reference signature."""
-from paella_b200.utils import sample  # noqa: F401
+from paella_b200.utils import load_conditional_models, sample  # noqa: F401

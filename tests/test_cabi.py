@@ -2,6 +2,7 @@
 entry points include/paella_b200.h declares; the ctypes table mirrors the header; the product never imports
 the oracle; no compute call is made here."""
 import ctypes
+import inspect
 import os
 import re
 
@@ -83,6 +84,25 @@ def test_python_mirror_has_reference_surface():
     import importlib
     for mod in ("src.vqgan", "utils.modules", "utils.alter_attention", "src.utils", "src.modules"):
         importlib.import_module(mod)
+
+
+def test_load_conditional_models_reads_reference_checkpoint_layout(tmp_path):
+    """ref/src/utils.py:24-32: `{'state_dict': ...}` VQGAN checkpoint -> eval-mode VQModel with those weights."""
+    import torch
+    from paella_b200 import utils, vqgan
+    src = vqgan.VQModel()
+    with torch.no_grad():
+        for p in src.parameters():
+            p.add_(0.01)
+    path = str(tmp_path / "vqgan_f4.pt")
+    torch.save({"state_dict": src.state_dict()}, path)
+    assert list(inspect.signature(utils.load_conditional_models).parameters) == ["byt5_model_name", "vqgan_path", "device"]
+    vq, byt5 = utils.load_conditional_models(None, path, "cpu")
+    assert byt5 is None and not vq.training and not any(p.requires_grad for p in vq.parameters())
+    for k, v in src.state_dict().items():
+        assert torch.equal(vq.state_dict()[k], v), k
+    import src.utils as shim
+    assert shim.load_conditional_models is utils.load_conditional_models
 
 
 def test_product_never_imports_oracle():
