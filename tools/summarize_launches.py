@@ -21,9 +21,10 @@ def main(src, dst, title):
         v = float(row[vi].replace(",", ""))
         v = {"ns": v / 1e3, "us": v, "usecond": v, "ms": v * 1e3, "s": v * 1e6}.get(row[ui], v)
         name = row[ki]
-        m = re.search(r"gemm_f16_kernel<(\d+), ?(?:\(pb200_epilogue\))?(\d+)(?:, ?(\d+))?", name)
+        name = name.replace("(int)", "").replace("(bool)", "")
+        m = re.search(r"(gemm_f16(?:_cg2)?_kernel)<(\d+), ?(\d+)(?:, ?(\d+))?", name)
         if m:
-            key = f"gemm_f16_kernel<BN={m.group(1)}, {EPI.get(int(m.group(2)), m.group(2))}" + (f", AMODE={m.group(3)}>" if m.group(3) else ">")
+            key = f"{m.group(1)}<BN={m.group(2)}, {EPI.get(int(m.group(3)), m.group(3))}" + (f", AMODE={m.group(4)}>" if m.group(4) else ">")
         else:
             key = re.sub(r"\(.*", "", re.sub(r"<.*", "", name)).replace("void ", "")
         agg[key][0] += 1
