@@ -216,6 +216,24 @@ def test_default_config_forward_vs_oracle(default_model):
     assert top1 > 0.97
 
 
+def test_default_config_forward_64x64_vs_oracle(default_model):
+    """SURVEY.md §8(d) cfg 4 geometry: 64x64 latents (Nq = 256 and 64 queries, Nk = 392 / 200 keys with clip_image),
+    several query tiles per (sample, head) in the attention kernel, 16x16 / 8x8 depthwise grids."""
+    from oracle import paella_oracle as po
+    from paella_b200.synth import synthetic_conditioning
+    m, sd = default_model
+    cond, _ = synthetic_conditioning(1, 128, with_clip_image=True)
+    x = torch.randint(0, 8192, (1, 64, 64), generator=torch.Generator().manual_seed(2))
+    r = torch.tensor([0.45])
+    want = po.paella_forward(sd, po.PaellaConfig(byt5_embd=2560), x, r, cond["byt5"], cond["clip"], cond["clip_image"])
+    got = m(x.to(DEV), r.to(DEV), cond["byt5"].to(DEV), clip=cond["clip"].to(DEV), clip_image=cond["clip_image"].to(DEV))
+    mx, rms = _errs(got, want)
+    top1 = float((got.cpu().argmax(1) == want.argmax(1)).float().mean())
+    _log("default_forward_64x64", {"max_abs": mx, "rms": rms, "logit_std": float(want.std()), "top1_agree": top1})
+    assert mx < MAX_ABS and rms < RMS
+    assert top1 > 0.97
+
+
 def test_default_config_sample_runs_and_is_seed_deterministic(default_model):
     from paella_b200 import utils as U
     from paella_b200.synth import synthetic_conditioning
