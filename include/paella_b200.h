@@ -98,7 +98,12 @@ enum pb200_epilogue {
     PB200_EPI_GELU_F16 = 2,   /* out fp16 = gelu_erf(acc + bias); sqsum[row/rows_per_sample, n] += out^2 */
     PB200_EPI_RESID_F32 = 3,  /* out fp32 = ((acc + bias)*alpha + resid) [* (1+film_a) + film_b]         */
     PB200_EPI_UNPATCH_F32 = 4,/* out fp32 NHWC [B,2h,2w,cout]: col=(dy,dx,co), row=(b,y,x); bias[col]    */
-    PB200_EPI_NCHW_F32 = 5    /* out fp32 [B, N, hw]: row=(b,p) -> out[b][n][p]; acc + bias              */
+    PB200_EPI_NCHW_F32 = 5,   /* out fp32 [B, N, hw]: row=(b,p) -> out[b][n][p]; acc + bias              */
+    /* LayerNorm folded across two GEMMs (the AttnBlock's pre-norm, ref/src/modules.py:78): the producer also emits
+     * the fp16 copy of its output row and the row statistics, the consumer multiplies the UN-normalised fp16 rows and
+     * normalises in its epilogue:  LN(x) W^T = rstd * (x W^T - mean * rowsum(W)). */
+    PB200_EPI_RESID_LN_F32 = 6, /* RESID_F32 + out16[M,ldo] = fp16(out); ln_stat[row] += (sum out, sum out^2)  */
+    PB200_EPI_F16_LN = 7       /* out fp16 = rstd[row]*(acc - mean[row]*ln_wsum[n]) + bias, stats from ln_stat */
 };
 
 typedef struct pb200_gemm_epilogue {
@@ -117,6 +122,11 @@ typedef struct pb200_gemm_epilogue {
     int64_t film_off;
     int remap_in, remap_out;   /* F16/F32: out_row = (row/remap_in)*remap_out + row%remap_in; 0 = identity */
     int up_h, up_w, up_cout;   /* UNPATCH: coarse grid and output channels */
+    void* out16;               /* RESID_LN: fp16 [M, ldo] copy of out */
+    int64_t* ln_stat;          /* RESID_LN (accumulated, caller zeroes) / F16_LN (read): [M][2] = (sum x * 2^20, sum x^2 * 2^16)
+                                  over the ln_c columns of a row, fixed point (integer atomics: order-independent) */
+    const float* ln_wsum;      /* F16_LN: [N] row sums of the fp16 weight matrix */
+    int ln_c;                  /* F16_LN: number of columns the statistics cover (= K of this GEMM) */
 } pb200_gemm_epilogue;
 
 int pb200_gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t m, int64_t n, int64_t k,

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libpaella_b200.so")
 
 PB200_MAX_LEVELS = 4
 
-EPI_F16, EPI_F32, EPI_GELU_F16, EPI_RESID_F32, EPI_UNPATCH_F32, EPI_NCHW_F32 = range(6)
+EPI_F16, EPI_F32, EPI_GELU_F16, EPI_RESID_F32, EPI_UNPATCH_F32, EPI_NCHW_F32, EPI_RESID_LN_F32, EPI_F16_LN = range(8)
 
 
 class GemmEpilogue(ctypes.Structure):
@@ -21,7 +21,8 @@ class GemmEpilogue(ctypes.Structure):
         ("mode", c_int), ("bias", c_void_p), ("out", c_void_p), ("ldo", c_int64), ("resid", c_void_p),
         ("ldr", c_int64), ("alpha", c_float), ("sqsum", c_void_p), ("rows_per_sample", c_int), ("film", c_void_p),
         ("film_ld", c_int64), ("film_off", c_int64), ("remap_in", c_int), ("remap_out", c_int), ("up_h", c_int),
-        ("up_w", c_int), ("up_cout", c_int),
+        ("up_w", c_int), ("up_cout", c_int), ("out16", c_void_p), ("ln_stat", c_void_p), ("ln_wsum", c_void_p),
+        ("ln_c", c_int),
     ]
 
 

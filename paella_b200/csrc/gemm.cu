@@ -94,6 +94,13 @@ template <int MODE>
 struct EpiPre {};
 template <>
 struct EpiPre<PB200_EPI_RESID_F32> { float4 r[8]; };
+template <>
+struct EpiPre<PB200_EPI_F16_LN> { float neg_mean = 0.f, rstd = 0.f; };     // this lane's row, computed once per tile
+template <>
+struct EpiPre<PB200_EPI_RESID_LN_F32> {
+    float4 r[8];
+    float ln_s = 0.f, ln_q = 0.f;      // this lane's row: sum / sum of squares over the chunks of the tile done so far
+};
 
 // Coalescing.  tcgen05.ld hands every lane one ROW of the chunk (32 consecutive columns), so a direct 16-byte store
 // per lane touches 32 different 128-byte lines per instruction and the LSU serialises them (measured: the fp32
@@ -157,8 +164,18 @@ __device__ __forceinline__ void store_chunk_f16(const float (&v)[32], __half* ou
 
 template <int MODE>
 __device__ __forceinline__ void epilogue_preload(const pb200_gemm_epilogue& ep, int M, int N, int row, int col0,
-                                                 EpiPre<MODE>& pre, int lane) {
-    if constexpr (MODE == PB200_EPI_RESID_F32) {
+                                                 EpiPre<MODE>& pre, int lane, bool first_chunk) {
+    if constexpr (MODE == PB200_EPI_F16_LN) {
+        if (first_chunk && row < M) {      // row statistics -> (mean, rstd), before the wait on the accumulator
+            const longlong2 st = *reinterpret_cast<const longlong2*>(ep.ln_stat + 2 * (int64_t)row);
+            const float inv_c = 1.0f / (float)ep.ln_c;
+            const float mean = (float)st.x * (1.0f / 1048576.0f) * inv_c;
+            const float ex2 = (float)st.y * (1.0f / 65536.0f) * inv_c;
+            pre.neg_mean = -mean;
+            pre.rstd = 1.0f / sqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-6f);
+        }
+    }
+    if constexpr (MODE == PB200_EPI_RESID_F32 || MODE == PB200_EPI_RESID_LN_F32) {
         const int col = col0 + (lane & 7) * 4;       // transposed layout: item i = row of lane (lane & 24) + i
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -170,11 +187,23 @@ __device__ __forceinline__ void epilogue_preload(const pb200_gemm_epilogue& ep, 
 
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, int M, int N, int row, int col0,
-                                               float (&v)[32], int lane, const EpiPre<MODE>& pre) {
+                                               float (&v)[32], int lane, EpiPre<MODE>& pre) {
     const bool row_ok = row < M;
     // warp-uniform: no column / row of this chunk is out of range -> the hot path carries no per-element predicates
     const bool full_cols = col0 + 32 <= N;
     const bool full = full_cols && __all_sync(0xffffffffu, row_ok);
+    // ---- folded LayerNorm of the A rows: acc = x W^T with x un-normalised; LN(x) W^T = rstd (acc - mean rowsum(W))
+    if constexpr (MODE == PB200_EPI_F16_LN) {
+        const float nm = pre.neg_mean, rstd = pre.rstd;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            if (col0 + g * 4 < N) {
+                const float4 ws = __ldg(reinterpret_cast<const float4*>(ep.ln_wsum + col0 + g * 4));
+                v[g * 4 + 0] = fmaf(nm, ws.x, v[g * 4 + 0]) * rstd; v[g * 4 + 1] = fmaf(nm, ws.y, v[g * 4 + 1]) * rstd;
+                v[g * 4 + 2] = fmaf(nm, ws.z, v[g * 4 + 2]) * rstd; v[g * 4 + 3] = fmaf(nm, ws.w, v[g * 4 + 3]) * rstd;
+            }
+        }
+    }
     // ---- bias (indexed by GEMM column in every mode)
     if (ep.bias) {
         if (full_cols) {
@@ -193,10 +222,10 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
             }
         }
     }
-    if (MODE == PB200_EPI_F16 || MODE == PB200_EPI_F32) {
+    if (MODE == PB200_EPI_F16 || MODE == PB200_EPI_F32 || MODE == PB200_EPI_F16_LN) {
         int64_t orow = row_ok ? row : -1;
         if (row_ok && ep.remap_in > 0) orow = (int64_t)(row / ep.remap_in) * ep.remap_out + (row % ep.remap_in);
-        if (MODE == PB200_EPI_F16) {
+        if (MODE == PB200_EPI_F16 || MODE == PB200_EPI_F16_LN) {
             store_chunk_f16(v, reinterpret_cast<__half*>(ep.out), ep.ldo, orow, col0, N, lane);
         } else {
             transpose8x8_f4(v, lane);
@@ -279,17 +308,22 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
                     if (col0 + j < N) atomicAdd(sq + (int64_t)(row / P) * N + col0 + j, fx(v[j]));
             }
         }
-    } else if (MODE == PB200_EPI_RESID_F32) {
+    } else if (MODE == PB200_EPI_RESID_F32 || MODE == PB200_EPI_RESID_LN_F32) {
         // (bias was added above in the row-per-lane layout); the rest runs in the transposed, coalesced layout
         transpose8x8_f4(v, lane);
         const int col = col0 + (lane & 7) * 4;
         float* obase = reinterpret_cast<float*>(ep.out);
+        float ls[8], lq[8];
+        if constexpr (MODE == PB200_EPI_RESID_LN_F32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ls[i] = lq[i] = 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = __shfl_sync(0xffffffffu, row, (lane & 24) + i);
             if (r < M && col < N) {
                 float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
-                if constexpr (MODE == PB200_EPI_RESID_F32) rr = pre.r[i];
+                if constexpr (MODE == PB200_EPI_RESID_F32 || MODE == PB200_EPI_RESID_LN_F32) rr = pre.r[i];
                 float4 y;
                 y.x = fmaf(v[i * 4 + 0], ep.alpha, rr.x); y.y = fmaf(v[i * 4 + 1], ep.alpha, rr.y);
                 y.z = fmaf(v[i * 4 + 2], ep.alpha, rr.z); y.w = fmaf(v[i * 4 + 3], ep.alpha, rr.w);
@@ -301,7 +335,32 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
                     y.z = fmaf(y.z, 1.0f + a.z, b.z); y.w = fmaf(y.w, 1.0f + a.w, b.w);
                 }
                 *reinterpret_cast<float4*>(obase + (int64_t)r * ep.ldo + col) = y;
+                if constexpr (MODE == PB200_EPI_RESID_LN_F32) {
+                    uint2 pk;
+                    pk.x = pack_half2(y.x, y.y);
+                    pk.y = pack_half2(y.z, y.w);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out16) + (int64_t)r * ep.ldo + col) = pk;
+                    ls[i] = (y.x + y.y) + (y.z + y.w);
+                    lq[i] = (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+                }
             }
+        }
+        if constexpr (MODE == PB200_EPI_RESID_LN_F32) {
+            // row statistics of the finished rows: item i of lane (a,b) is row 8a+i, columns 4b..4b+3 -> transpose-reduce
+            // over the 8 lanes of the group; lane 8a+b ends with the sums of row 8a+b, i.e. of its own `row`
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int i = 0; i < o; ++i) {
+                    const float s_send = up ? ls[i] : ls[i + o], s_keep = up ? ls[i + o] : ls[i];
+                    const float q_send = up ? lq[i] : lq[i + o], q_keep = up ? lq[i + o] : lq[i];
+                    ls[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, o);
+                    lq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, o);
+                }
+            }
+            pre.ln_s += ls[0];          // flushed once per tile by epilogue_finish (one atomic pair per row and warp)
+            pre.ln_q += lq[0];
         }
     } else if (MODE == PB200_EPI_UNPATCH_F32) {
         if (!row_ok) return;
@@ -327,6 +386,18 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
 #pragma unroll
         for (int j = 0; j < 32; ++j)
             if (col0 + j < N) o[(int64_t)j * hw] = v[j];
+    }
+}
+
+// after the last chunk of a tile: flush what the chunks accumulated per row
+template <int MODE>
+__device__ __forceinline__ void epilogue_finish(const pb200_gemm_epilogue& ep, int M, int row, EpiPre<MODE>& pre) {
+    if constexpr (MODE == PB200_EPI_RESID_LN_F32) {
+        if (row < M) {
+            unsigned long long* st = reinterpret_cast<unsigned long long*>(ep.ln_stat) + 2 * (int64_t)row;
+            atomicAdd(st, (unsigned long long)__float2ll_rn(pre.ln_s * 1048576.0f));
+            atomicAdd(st + 1, (unsigned long long)__float2ll_rn(pre.ln_q * 65536.0f));
+        }
     }
 }
 
@@ -494,17 +565,18 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                           : M;      // M = B*oh*ow: out of range -> masked
             }
             EpiPre<MODE> pre;
-            if (n_idx + half * COLS_PER_WARP < N) epilogue_preload<MODE>(ep, M, N, row, n_idx + half * COLS_PER_WARP, pre, lane);
+            if (n_idx + half * COLS_PER_WARP < N) epilogue_preload<MODE>(ep, M, N, row, n_idx + half * COLS_PER_WARP, pre, lane, true);
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
 #pragma unroll 1
             for (int c = half * COLS_PER_WARP; c < (half + 1) * COLS_PER_WARP; c += 32) {
                 if (n_idx + c >= N) break;
-                if (c != half * COLS_PER_WARP) epilogue_preload<MODE>(ep, M, N, row, n_idx + c, pre, lane);
+                if (c != half * COLS_PER_WARP) epilogue_preload<MODE>(ep, M, N, row, n_idx + c, pre, lane, false);
                 float v[32];
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c), v);
                 epilogue_chunk<MODE>(ep, M, N, row, n_idx + c, v, lane, pre);
             }
+            epilogue_finish<MODE>(ep, M, row, pre);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
@@ -686,17 +758,18 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const int c_end = min((slice + 1) * COLS_PER_WARP, un.width);      // a narrow tile leaves the upper slices idle
             EpiPre<MODE> pre;
             if (slice * COLS_PER_WARP < c_end && n_idx + slice * COLS_PER_WARP < N)
-                epilogue_preload<MODE>(ep, M, N, row, n_idx + slice * COLS_PER_WARP, pre, lane);
+                epilogue_preload<MODE>(ep, M, N, row, n_idx + slice * COLS_PER_WARP, pre, lane, true);
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
 #pragma unroll 1
             for (int c = slice * COLS_PER_WARP; c < c_end; c += 32) {
                 if (n_idx + c >= N) break;
-                if (c != slice * COLS_PER_WARP) epilogue_preload<MODE>(ep, M, N, row, n_idx + c, pre, lane);
+                if (c != slice * COLS_PER_WARP) epilogue_preload<MODE>(ep, M, N, row, n_idx + c, pre, lane, false);
                 float v[32];
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c), v);
                 epilogue_chunk<MODE>(ep, M, N, row, n_idx + c, v, lane, pre);
             }
+            epilogue_finish<MODE>(ep, M, row, pre);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(leader_tempty0 + 8u * as);
@@ -752,6 +825,8 @@ static int launch_cg2_mode(const CUtensorMap& ta, const CUtensorMap& tb, const C
         case PB200_EPI_RESID_F32: return launch_cg2<BLOCK_N, PB200_EPI_RESID_F32>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
         case PB200_EPI_UNPATCH_F32: return launch_cg2<BLOCK_N, PB200_EPI_UNPATCH_F32>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
         case PB200_EPI_NCHW_F32: return launch_cg2<BLOCK_N, PB200_EPI_NCHW_F32>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
+        case PB200_EPI_RESID_LN_F32: return launch_cg2<BLOCK_N, PB200_EPI_RESID_LN_F32>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
+        case PB200_EPI_F16_LN: return launch_cg2<BLOCK_N, PB200_EPI_F16_LN>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
     }
     PB_CHECK(false, "gemm: unknown epilogue mode %d", ep.mode);
     return 1;
@@ -832,6 +907,8 @@ static int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const pb200
         case PB200_EPI_RESID_F32: return launch_cfg<BLOCK_N, PB200_EPI_RESID_F32>(ta, tb, ep, M, N, K, st);
         case PB200_EPI_UNPATCH_F32: return launch_cfg<BLOCK_N, PB200_EPI_UNPATCH_F32>(ta, tb, ep, M, N, K, st);
         case PB200_EPI_NCHW_F32: return launch_cfg<BLOCK_N, PB200_EPI_NCHW_F32>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_RESID_LN_F32: return launch_cfg<BLOCK_N, PB200_EPI_RESID_LN_F32>(ta, tb, ep, M, N, K, st);
+        case PB200_EPI_F16_LN: return launch_cfg<BLOCK_N, PB200_EPI_F16_LN>(ta, tb, ep, M, N, K, st);
     }
     PB_CHECK(false, "gemm: unknown epilogue mode %d", ep.mode);
     return 1;
@@ -903,15 +980,20 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const
     PB_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem");
     PB_CHECK(N % 8 == 0, "gemm: N=%lld must be a multiple of 8", (long long)N);
     PB_CHECK(ep.out != nullptr, "gemm: null output");
-    if (ep.mode == PB200_EPI_RESID_F32) PB_CHECK(ep.resid != nullptr, "gemm: RESID epilogue without resid");
+    if (ep.mode == PB200_EPI_RESID_F32 || ep.mode == PB200_EPI_RESID_LN_F32)
+        PB_CHECK(ep.resid != nullptr, "gemm: RESID epilogue without resid");
+    if (ep.mode == PB200_EPI_RESID_LN_F32) PB_CHECK(ep.out16 && ep.ln_stat, "gemm: RESID_LN needs out16 and ln_stat");
+    if (ep.mode == PB200_EPI_F16_LN)
+        PB_CHECK(ep.ln_stat && ep.ln_wsum && ep.ln_c > 0, "gemm: F16_LN needs ln_stat, ln_wsum and ln_c");
     if (ep.mode == PB200_EPI_UNPATCH_F32)
         PB_CHECK(ep.up_cout % 8 == 0 && ep.up_cout * 4 == N && (int64_t)ep.up_h * ep.up_w > 0,
                  "gemm: bad un-patchify geometry");
-    if ((ep.mode == PB200_EPI_GELU_F16 && ep.sqsum) || (ep.mode == PB200_EPI_RESID_F32 && ep.film) ||
+    if ((ep.mode == PB200_EPI_GELU_F16 && ep.sqsum) || ((ep.mode == PB200_EPI_RESID_F32 || ep.mode == PB200_EPI_RESID_LN_F32) && ep.film) ||
         ep.mode == PB200_EPI_NCHW_F32)
         PB_CHECK(ep.rows_per_sample > 0, "gemm: rows_per_sample required");
-    static const char* kTags[6] = {"gemm_f16", "gemm_f32", "gemm_gelu_sqsum", "gemm_resid", "gemm_unpatch", "gemm_nchw"};
-    ProfScope prof(ep.mode >= 0 && ep.mode < 6 ? kTags[ep.mode] : "gemm", 2.0 * (double)M * (double)N * (double)K, st);
+    static const char* kTags[8] = {"gemm_f16", "gemm_f32", "gemm_gelu_sqsum", "gemm_resid", "gemm_unpatch", "gemm_nchw",
+                                   "gemm_resid", "gemm_f16"};
+    ProfScope prof(ep.mode >= 0 && ep.mode < 8 ? kTags[ep.mode] : "gemm", 2.0 * (double)M * (double)N * (double)K, st);
     if (gemm_use_cg2(M) && block_n >= 128) {
         const int tbn = tail ? tail->bn : 0;
         const CUtensorMap* ttb = tail ? tail->tb : nullptr;

@@ -71,6 +71,16 @@ __global__ void pack_kernel(const float* __restrict__ src, void* __restrict__ ds
     }
 }
 
+// out[r] = sum_k fp32(w[r, k]) of a packed fp16 matrix (warp per row): the rowsum(W) of the folded LayerNorm
+__global__ void __launch_bounds__(256) rowsum_f16_kernel(const __half* __restrict__ w, int rows, int cols, float* __restrict__ out) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int k = lane; k < cols; k += 32) s += __half2float(w[(int64_t)r * cols + k]);
+    s = warp_sum(s);
+    if (lane == 0) out[r] = s;
+}
+
 struct ParamSpec {
     std::string name;
     int64_t numel;      // reference tensor numel
@@ -78,6 +88,8 @@ struct ParamSpec {
     int64_t dst_off;    // bytes into the blob
     int64_t dst_numel;
     int d0, d1, d2;
+    int64_t rowsum_off = -1;     // fp32 [rowsum_rows]: row sums of the packed fp16 matrix [rowsum_rows, rowsum_cols]
+    int rowsum_rows = 0, rowsum_cols = 0;
 };
 
 enum BlockKind { BK_RES, BK_TIME, BK_ATTN, BK_FF, BK_DOWN, BK_UP, BK_SAVE };
@@ -88,7 +100,9 @@ struct BlockPlan {
     int64_t film_off = -1;          // RES/FF: fused FiLM of the following TimestepBlock; TIME: own offset
     bool film_fused = false;        // TIME: already applied by the previous block's epilogue
     int64_t kvm_w = -1, kvm_b = -1, inproj_w = -1, inproj_b = -1, outproj_w = -1, outproj_b = -1;
+    int64_t inproj_wsum = -1;       // ATTN: row sums of in_proj_weight (LayerNorm folded into the QKV GEMM)
     int attn_index = -1;
+    int ln_fold_attn = -1;          // RES/FF: index of the AttnBlock that directly consumes this block's output, or -1
     int64_t rs_w = -1, rs_b = -1;
 };
 
@@ -236,6 +250,13 @@ static int build_plan(pb200_paella* m) {
             b.kind = BK_ATTN;
             PB_CHECK(c.nhead[lvl] > 0 && ch % c.nhead[lvl] == 0, "level %d: nhead %d does not divide %d", lvl, c.nhead[lvl], ch);
             b.inproj_w = m->f16(pre + "attention.attn.in_proj_weight", (int64_t)3 * ch * ch);
+            {   // derived: fp32 row sums of the fp16 matrix, filled when the parameter is loaded
+                ParamSpec& ps = m->params.back();
+                ps.rowsum_off = m->weight_bytes;
+                ps.rowsum_rows = 3 * ch; ps.rowsum_cols = ch;
+                m->weight_bytes += ((int64_t)3 * ch * 4 + 255) / 256 * 256;
+                b.inproj_wsum = ps.rowsum_off;
+            }
             b.inproj_b = m->f32(pre + "attention.attn.in_proj_bias", 3 * ch);
             b.outproj_w = m->f16(pre + "attention.attn.out_proj.weight", (int64_t)ch * ch);
             b.outproj_b = m->f32(pre + "attention.attn.out_proj.bias", ch);
@@ -294,6 +315,8 @@ static int build_plan(pb200_paella* m) {
     }
     PB_CHECK(film_cursor == film_rows / 2 || film_cursor == film_rows, "internal: FiLM row count mismatch");
     m->film_total = film_cursor;
+    // (below, after the FiLM fusion:) a ResBlock/FeedForwardBlock whose output -- after its fused TimestepBlock, if any --
+    // goes straight into an AttnBlock also produces that block's LayerNorm inputs (fp16 rows + row statistics)
     // fuse each TimestepBlock that directly follows a ResBlock/FeedForwardBlock into that block's GEMM epilogue
     for (size_t i = 0; i + 1 < m->blocks.size(); ++i) {
         BlockPlan& a = m->blocks[i];
@@ -302,6 +325,15 @@ static int build_plan(pb200_paella* m) {
             a.film_off = t.film_off;
             t.film_fused = true;
         }
+    }
+    static const bool no_fold = getenv("PB200_NO_LN_FOLD") != nullptr;      // A/B knob
+    for (size_t i = 0; !no_fold && i + 1 < m->blocks.size(); ++i) {
+        BlockPlan& a = m->blocks[i];
+        if (a.kind != BK_RES && a.kind != BK_FF) continue;
+        size_t j = i + 1;
+        if (m->blocks[j].kind == BK_TIME && m->blocks[j].film_fused) ++j;
+        if (j < m->blocks.size() && m->blocks[j].kind == BK_ATTN && m->blocks[j].level == a.level)
+            a.ln_fold_attn = m->blocks[j].attn_index;
     }
     return 0;
 }
@@ -323,6 +355,8 @@ struct FeatWs {
     float* xu[PB200_MAX_LEVELS];
     __half *a16, *h16, *qkv16, *o16;
     uint64_t *gsq, *gscale;      // GRN statistic ping/pong (2^-24 fixed point)
+    int64_t* lnstat;             // folded LayerNorm: per AttnBlock [M][2] fixed-point row statistics
+    int64_t lnstat_stride;       // int64 elements per AttnBlock
     float *r_emb, *film, *y;
 };
 
@@ -343,6 +377,13 @@ static void plan_features(const pb200_paella* m, int Bt, int H, int W, Arena& ar
     ws.o16 = ar.take<__half>(max_mc);
     ws.gsq = ar.take<uint64_t>((int64_t)Bt * 4 * m->max_c);     // ping
     ws.gscale = ar.take<uint64_t>((int64_t)Bt * 4 * m->max_c);  // pong (second GRN statistic buffer)
+    {
+        int64_t max_m = 0;
+        for (const BlockPlan& b : m->blocks)
+            if (b.kind == BK_ATTN) { const int64_t M = (int64_t)Bt * (P >> (2 * b.level)); max_m = M > max_m ? M : max_m; }
+        ws.lnstat_stride = 2 * max_m;
+        ws.lnstat = ar.take<int64_t>(ws.lnstat_stride * (m->n_attn > 0 ? m->n_attn : 1));
+    }
     ws.r_emb = ar.take<float>((int64_t)Bt * c.c_r);
     ws.film = ar.take<float>((int64_t)Bt * (m->film_total > 0 ? m->film_total : 4));
     ws.y = ar.take<float>((int64_t)Bt * H * W * c.c_out);
@@ -423,6 +464,12 @@ int pb200_paella_load_param(pb200_paella* m, const char* name, const float* src,
     pack_kernel<<<ceil_div(p.dst_numel, 256), 256, 0, (cudaStream_t)stream>>>(src, m->blob + p.dst_off, p.kind, p.dst_numel,
                                                                              p.d0, p.d1, p.d2);
     PB_LAUNCH_CHECK();
+    if (p.rowsum_off >= 0) {
+        rowsum_f16_kernel<<<ceil_div(p.rowsum_rows, 8), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const __half*>(m->blob + p.dst_off), p.rowsum_rows, p.rowsum_cols,
+            reinterpret_cast<float*>(m->blob + p.rowsum_off));
+        PB_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -572,6 +619,8 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
                                 cudaMemcpyDeviceToDevice, st));
     PB_CUDA(cudaMemsetAsync(ws.gsq, 0, (size_t)Bt * 4 * m->max_c * sizeof(uint64_t), st));
     if (Bc < Bt) PB_CUDA(cudaMemsetAsync(ws.gscale, 0, (size_t)Bt * 4 * m->max_c * sizeof(uint64_t), st));
+    if (m->n_attn > 0) PB_CUDA(cudaMemsetAsync(ws.lnstat, 0, (size_t)ws.lnstat_stride * m->n_attn * sizeof(int64_t), st));
+    int ln_ready = -1;             // AttnBlock index whose fp16 input rows (a16) + row statistics the last block produced
     uint64_t* grn_stat[2] = {ws.gsq, ws.gscale};      // ping-pong: the GRN kernel of block i zeroes the buffer of block i+1
     int grn_flip = 0;
 
@@ -587,10 +636,17 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
     float* x = ws.xd[0];
     bool up_phase = false;
     // replicate the shared prefix: x (= xd[l] on the down path) and every saved level output below it
-    auto replicate = [&](int level) -> int {
+    auto replicate = [&](int level, int attn_index) -> int {
         for (int q = 0; q <= level; ++q) {
             const size_t n = (size_t)Bc * gh[q] * gw[q] * c.c_hidden[q];
             PB_CUDA(cudaMemcpyAsync(ws.xd[q] + n, ws.xd[q], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        if (attn_index >= 0 && ln_ready == attn_index) {   // the folded-LayerNorm inputs of the AttnBlock that starts here
+            const size_t rows = (size_t)Bc * gh[level] * gw[level];
+            PB_CUDA(cudaMemcpyAsync(ws.a16 + rows * c.c_hidden[level], ws.a16, rows * c.c_hidden[level] * sizeof(__half),
+                                    cudaMemcpyDeviceToDevice, st));
+            int64_t* stat = ws.lnstat + ws.lnstat_stride * ln_ready;
+            PB_CUDA(cudaMemcpyAsync(stat + 2 * rows, stat, 2 * rows * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
         }
         Bc = Bt;
         return 0;
@@ -599,7 +655,7 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
         const BlockPlan& b = m->blocks[bi];
         const int l = b.level, ch = b.c, P = gh[l] * gw[l];
         // the prefix ends at the first AttnBlock, or where the up path starts (its tensors live outside xd[])
-        if (Bc < Bt && (b.kind == BK_ATTN || b.kind == BK_UP || (b.kind == BK_SAVE && l == L - 1))) PB_TRY(replicate(l));
+        if (Bc < Bt && (b.kind == BK_ATTN || b.kind == BK_UP || (b.kind == BK_SAVE && l == L - 1))) PB_TRY(replicate(l, b.kind == BK_ATTN ? b.attn_index : -1));
         const int64_t M = (int64_t)Bc * P;
         switch (b.kind) {
             case BK_SAVE:
@@ -637,9 +693,16 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
                 e1.sqsum = stat; e1.rows_per_sample = P;
                 PB_TRY(m->gemm(ws.a16, ch, M, ch, b.w1, 4 * (int64_t)ch, e1, st));
                 PB_TRY(launch_grn_fused(ws.h16, Bc, P, 4 * ch, stat, stat_next, 4 * m->max_c, m->w<float>(b.gamma), m->w<float>(b.beta), st));
-                pb200_gemm_epilogue e2 = epi(PB200_EPI_RESID_F32, m->w<float>(b.b2), x, ch);
+                // the next AttnBlock's LayerNorm is folded into its QKV GEMM when this block feeds it directly
+                const bool fold = b.ln_fold_attn >= 0;
+                pb200_gemm_epilogue e2 = epi(fold ? PB200_EPI_RESID_LN_F32 : PB200_EPI_RESID_F32, m->w<float>(b.b2), x, ch);
                 e2.resid = x; e2.ldr = ch; e2.rows_per_sample = P;
                 if (b.film_off >= 0) { e2.film = ws.film; e2.film_ld = m->film_total; e2.film_off = b.film_off; }
+                if (fold) {
+                    e2.out16 = ws.a16;
+                    e2.ln_stat = ws.lnstat + ws.lnstat_stride * b.ln_fold_attn;
+                    ln_ready = b.ln_fold_attn;
+                }
                 PB_TRY(m->gemm(ws.h16, 4 * (int64_t)ch, M, 4 * (int64_t)ch, b.w2, ch, e2, st));
                 break;
             }
@@ -647,8 +710,15 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
                 if (!b.film_fused) PB_TRY(launch_film_apply(x, M, ch, P, ws.film, m->film_total, b.film_off, st));
                 break;
             case BK_ATTN: {
-                PB_TRY(launch_ln_rows(x, M, ch, 1.0f, 0.0f, ws.a16, nullptr, st));
-                pb200_gemm_epilogue e1 = epi(PB200_EPI_F16, m->w<float>(b.inproj_b), ws.qkv16, 3 * ch);
+                const bool folded = ln_ready == b.attn_index;
+                pb200_gemm_epilogue e1 = epi(folded ? PB200_EPI_F16_LN : PB200_EPI_F16, m->w<float>(b.inproj_b), ws.qkv16, 3 * ch);
+                if (folded) {       // a16 = fp16(x) and the row statistics came out of the previous GEMM's epilogue
+                    e1.ln_stat = ws.lnstat + ws.lnstat_stride * b.attn_index;
+                    e1.ln_wsum = m->w<float>(b.inproj_wsum);
+                    e1.ln_c = ch;
+                } else {
+                    PB_TRY(launch_ln_rows(x, M, ch, 1.0f, 0.0f, ws.a16, nullptr, st));
+                }
                 PB_TRY(m->gemm(ws.a16, ch, M, ch, b.inproj_w, 3 * (int64_t)ch, e1, st));
                 AttnParams ap;
                 ap.qkv = ws.qkv16;

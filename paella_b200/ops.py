@@ -126,7 +126,8 @@ def vq_gather(idx: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
 
 # ------------------------------------------------------------------ GEMM (unit-test surface)
 def gemm_f16(a: torch.Tensor, w: torch.Tensor, mode: int, out: torch.Tensor, bias=None, resid=None, alpha: float = 1.0,
-             sqsum=None, rows_per_sample: int = 0, film=None, film_off: int = 0, remap=(0, 0), up=(0, 0, 0)) -> torch.Tensor:
+             sqsum=None, rows_per_sample: int = 0, film=None, film_off: int = 0, remap=(0, 0), up=(0, 0, 0), out16=None,
+             ln_stat=None, ln_wsum=None) -> torch.Tensor:
     """out = epilogue(a[M,K] @ w[N,K]^T); a, w fp16 contiguous."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.shape[1] == w.shape[1]
     M, K = a.shape
@@ -135,7 +136,12 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, mode: int, out: torch.Tensor, bia
     ep.mode = mode
     ep.bias = ptr(bias).value if bias is not None else None
     ep.out = ptr(out).value
-    ep.ldo = out.shape[-1] if mode in (_lib.EPI_F16, _lib.EPI_F32, _lib.EPI_GELU_F16, _lib.EPI_RESID_F32) else 0
+    ep.ldo = out.shape[-1] if mode in (_lib.EPI_F16, _lib.EPI_F32, _lib.EPI_GELU_F16, _lib.EPI_RESID_F32, _lib.EPI_RESID_LN_F32,
+                                       _lib.EPI_F16_LN) else 0
+    ep.out16 = ptr(out16).value if out16 is not None else None
+    ep.ln_stat = ptr(ln_stat).value if ln_stat is not None else None
+    ep.ln_wsum = ptr(ln_wsum).value if ln_wsum is not None else None
+    ep.ln_c = K if mode == _lib.EPI_F16_LN else 0
     ep.resid = ptr(resid).value if resid is not None else None
     ep.ldr = resid.shape[-1] if resid is not None else 0
     ep.alpha = alpha

@@ -258,6 +258,46 @@ def test_gemm_resid_film_inplace(M, N, K, P):
     assert err < 3e-3
 
 
+@pytest.mark.parametrize("M,C,N,P", [(8192, 1280, 3840, 64), (1024, 128, 384, 16), (300, 64, 96, 100)])
+def test_gemm_layernorm_folded_across_two_gemms(M, C, N, P):
+    """RESID_LN producer (fp32 x, fp16 copy, fixed-point row statistics) + F16_LN consumer:
+    consumer(fp16(x)) == LayerNorm(x) @ W^T + b within the fp16-operand tolerance."""
+    from paella_b200 import _lib
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(11)
+    K1 = 256
+    a = torch.randn(M, K1, device=DEV, generator=g).half()
+    w1 = (torch.randn(C, K1, device=DEV, generator=g) / math.sqrt(K1)).half()
+    b1 = torch.randn(C, device=DEV, generator=g)
+    x0 = torch.randn(M, C, device=DEV, generator=g) * 2 + 0.7          # non-zero row means
+    film = torch.randn(M // P if M % P == 0 else 1, 2 * C, device=DEV, generator=g) * 0.1
+    use_film = M % P == 0
+    y = _ref_mm(a, w1) + b1 + x0
+    if use_film:
+        y = (y.view(M // P, P, C) * (1 + film[:, None, :C]) + film[:, None, C:]).view(M, C)
+    x = x0.clone()
+    x16 = torch.full((M, C), float("nan"), device=DEV, dtype=torch.float16)
+    stat = torch.zeros(M, 2, device=DEV, dtype=torch.int64)
+    ops.gemm_f16(a, w1, _lib.EPI_RESID_LN_F32, x, bias=b1, resid=x, rows_per_sample=P if use_film else 0,
+                 film=film if use_film else None, out16=x16, ln_stat=stat)
+    assert float((x - y).abs().max()) < 5e-3
+    assert torch.equal(x16, x.half())
+    s_ref, q_ref = x.double().sum(1), (x.double() ** 2).sum(1)
+    assert float((stat[:, 0].double() / 2 ** 20 - s_ref).abs().max()) < 1e-2
+    assert float(((stat[:, 1].double() / 2 ** 16 - q_ref).abs() / q_ref).max()) < 1e-4
+    # consumer
+    w2 = (torch.randn(N, C, device=DEV, generator=g) / math.sqrt(C)).half()
+    b2 = torch.randn(N, device=DEV, generator=g) * 0.1
+    wsum = w2.float().sum(1).contiguous()
+    want = torch.nn.functional.layer_norm(x, (C,), eps=1e-6) @ w2.float().t() + b2
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
+    ops.gemm_f16(x16, w2, _lib.EPI_F16_LN, out, bias=b2, ln_stat=stat, ln_wsum=wsum)
+    err = float((out.float() - want).abs().max())
+    rms = float((out.float() - want).pow(2).mean().sqrt())
+    _log("gemm_ln_fold", {"M": M, "C": C, "N": N, "max_abs_err": err, "rms": rms})
+    assert err < 3e-2 and rms < 4e-3, (err, rms)
+
+
 def test_gemm_unpatchify_and_nchw_and_remap():
     from paella_b200 import _lib
     ops = _ops()
