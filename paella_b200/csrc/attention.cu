@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     constexpr int CPR = HD / 8;           // 16-byte chunks per row
     constexpr int QROWS = ATT_BM;
     constexpr int n_buf = 2;
+    pdl_launch_dependents();
     extern __shared__ __align__(16) __half smem_att[];
     __half* sQ = smem_att;                                   // [QROWS][LDS]
     __half* sKb = smem_att + QROWS * LDS;                     // [n_buf][ATT_BN][LDS]

@@ -63,6 +63,10 @@ struct ProfScope {
 };
 
 // ---------------------------------------------------------------- small device helpers
+// Lets a dependent kernel launched with programmatic stream serialization (the tcgen05 GEMMs, see ptx.cuh) start its
+// prologue while this kernel's last CTAs are still running.  No effect otherwise.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

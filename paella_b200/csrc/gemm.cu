@@ -677,6 +677,10 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     ptx::tc_fence_after();
     ptx::cluster_sync();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // everything above overlapped the tail of the previous kernel (programmatic dependent launch); its results are
+    // read from here on
+    ptx::griddep_launch();
+    ptx::griddep_wait();
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -803,13 +807,16 @@ static int launch_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     cfg.blockDim = dim3(gemm_threads(BLOCK_N));
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    static const bool pdl = getenv("PB200_NO_PDL") == nullptr;      // A/B knob
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 2 : 1;
     PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_cg2_kernel<BLOCK_N, MODE>, ta, tb, *tb_tail, ep, M, N, K, n_main, tail_bn));
     PB_LAUNCH_CHECK();
     return 0;

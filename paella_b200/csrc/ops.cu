@@ -71,6 +71,7 @@ template <bool PATCHIFY>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, int64_t rows, int C, float scale,
                                                       float shift, __half* __restrict__ out16, float* __restrict__ out32,
                                                       int h, int w) {
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(128) dwconv_ln_kernel(const float* __restrict_
                                                         int B, int h, int w, int c, int k, __half* __restrict__ out) {
     // one CTA = a 2x2 patch of positions of one sample (4 warps, small CTAs for occupancy: measured on B200, 16-warp
     // 4x4 patches were 18% slower); the four 3x3 halos overlap so half of the tap rows come from L1
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int pw = (w + 1) >> 1, ph = (h + 1) >> 1;
     const int b = blockIdx.x / (pw * ph);
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 320 ? 2 : 1)) dwconv3_ln_patch_
                                                                 int B, int h, int w, int c, __half* __restrict__ out) {
     __shared__ float red[32 * DW_NPOS];
     __shared__ float tot[2][DW_NPOS];
+    pdl_launch_dependents();
     const int q = threadIdx.x, nvq = c >> 2;
     const bool active = q < nvq;
     const int qc = active ? q : 0;                       // idle threads shadow chunk 0 and never store
@@ -436,6 +439,7 @@ __device__ __forceinline__ float grn_fx(unsigned long long q) { return __ull2flo
 __global__ void __launch_bounds__(384) grn_fused_kernel(__half* __restrict__ h, int P, int N, const unsigned long long* __restrict__ sq,
                                                         unsigned long long* __restrict__ sq_next, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int rows_per_cta, int zero_per_sample) {
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const unsigned long long* sqb = sq + (int64_t)b * N;
     float s = 0.f;

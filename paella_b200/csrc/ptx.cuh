@@ -59,6 +59,13 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(v));
     return v;
 }
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// (block scheduling, barrier / TMEM setup) while its predecessor in the stream is still draining; it must execute
+// griddep_wait() before touching anything the predecessor wrote.  griddep_launch() in a kernel lets its dependent start
+// early.  Both are no-ops when the launch carries no such dependency.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void cluster_sync() {     // all threads of all CTAs of the cluster
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
