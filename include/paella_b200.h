@@ -131,6 +131,10 @@ typedef struct pb200_gemm_epilogue {
 
 int pb200_gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t m, int64_t n, int64_t k,
                    const pb200_gemm_epilogue* epi, void* stream);
+/* Host-side tile plan pb200_gemm_f16 would use for an [m,k] x [n,k]^T problem on `sm_count` multiprocessors (0 = the
+ * current device, or 148 without one): BLOCK_N, whether the 2-SM (cta_group::2) kernel runs it, and the column width
+ * of the narrow tail tiles (0 = none).  Pure arithmetic, no device work. */
+int pb200_gemm_plan(int64_t m, int64_t n, int64_t k, int sm_count, int* block_n, int* two_sm, int* tail_block_n);
 
 /* ------------------------------------------------------------------------------------------
  * Block-level kernels: what the reference's building-block modules (ref/src/modules.py:7-106)

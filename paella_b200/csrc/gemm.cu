@@ -921,13 +921,19 @@ static int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const pb200
     return 1;
 }
 
+// planning-only override of the multiprocessor count (pb200_gemm_plan); 0 = ask the device
+static thread_local int g_plan_sms = 0;
+static int plan_sm_count() {
+    if (g_plan_sms > 0) return g_plan_sms;
+    const int s = sm_count();
+    return s > 0 ? s : 148;
+}
+
 static bool gemm_use_cg2(int64_t M) {
-    // The 2-SM kernel is numerically verified (tests pass with PB200_CG2=1) but measured SLOWER than the 1-SM kernel
-    // on B200 (551 vs 907 TFLOP/s on 8192x5120x1280): opt-in until its pipeline is fixed.
-    static const bool on = getenv("PB200_CG2") != nullptr;
+    // The 2-SM kernel takes every problem with more than one 128-row tile (1243 vs 1095 TFLOP/s on 8192x3840x1280 once
+    // its producer stopped issuing MEMBAR.ALL.GPU per k-block, profiles/r01_cg2_gemm_notes.md); PB200_NO_CG2 disables it.
     static const bool off = getenv("PB200_NO_CG2") != nullptr;
-    (void)on;
-    return !off && M > GEMM_BLOCK_M && sm_count() % 2 == 0;
+    return !off && M > GEMM_BLOCK_M && plan_sm_count() % 2 == 0;
 }
 
 int gemm_pick_block_n(int64_t M, int64_t N, int64_t K, bool allow_cg2) {
@@ -939,7 +945,7 @@ int gemm_pick_block_n(int64_t M, int64_t N, int64_t K, bool allow_cg2) {
     // and pick the minimum.  The 2-SM kernel's work unit is a 256-row pair tile on sm_count/2 pairs.
     static const int force = getenv("PB200_FORCE_BN") ? atoi(getenv("PB200_FORCE_BN")) : 0;   // experiments only
     if (force == 64 || force == 128 || force == 256) return force;
-    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int sms = plan_sm_count();
     const bool cg2 = allow_cg2 && gemm_use_cg2(M);
     const long n_kb = K > 0 ? (long)ceil_div(K, GEMM_BLOCK_K) : 16;
     const int cands[3] = {256, 128, 64};
@@ -965,7 +971,7 @@ int gemm_tail_block_n(int64_t M, int64_t N, int block_n) {
     // gemm_pick_block_n), hence the 0.55 / 0.45 weights; measured on 8192 x 1280 x {1280, 5120}.
     static const int force = getenv("PB200_GEMM_TAIL") ? atoi(getenv("PB200_GEMM_TAIL")) : -1;   // 0 disables, 64/128 force
     if (!gemm_use_cg2(M) || block_n != 256) return 0;
-    const long workers = sm_count() / 2;
+    const long workers = plan_sm_count() / 2;
     const long n_big = (long)ceil_div(M, 2 * GEMM_BLOCK_M) * ceil_div(N, block_n);
     const long rem = n_big % workers;
     if (n_big < workers || rem == 0) return 0;
@@ -1029,6 +1035,17 @@ int gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, 
 }
 
 }  // namespace pb
+
+extern "C" int pb200_gemm_plan(int64_t m, int64_t n, int64_t k, int sm_count, int* block_n, int* two_sm, int* tail_block_n) {
+    PB_CHECK(m > 0 && n > 0 && k > 0 && block_n && two_sm && tail_block_n, "gemm_plan: bad arguments");
+    pb::g_plan_sms = sm_count > 0 ? sm_count : 0;
+    const int bn = pb::gemm_pick_block_n(m, n, k);
+    *block_n = bn;
+    *two_sm = pb::gemm_use_cg2(m) && bn >= 128 ? 1 : 0;
+    *tail_block_n = pb::gemm_tail_block_n(m, n, bn);
+    pb::g_plan_sms = 0;
+    return 0;
+}
 
 extern "C" int pb200_gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t m, int64_t n, int64_t k,
                               const pb200_gemm_epilogue* epi, void* stream) {

@@ -105,6 +105,35 @@ def test_load_conditional_models_reads_reference_checkpoint_layout(tmp_path):
     assert shim.load_conditional_models is utils.load_conditional_models
 
 
+def test_gemm_tile_plan_on_a_148_sm_part():
+    """Host-side tile planner (pure arithmetic, no device work): which kernel / BLOCK_N / tail width the bench
+    workload's GEMM shapes get on a 148-SM B200."""
+    import ctypes
+    from paella_b200 import _lib
+    L = _lib.lib()
+
+    def plan(m, n, k, sms=148):
+        bn, two, tail = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(L.pb200_gemm_plan(m, n, k, sms, ctypes.byref(bn), ctypes.byref(two), ctypes.byref(tail)), "gemm_plan")
+        return bn.value, two.value, tail.value
+    # level-1 MLP GEMM2 / out-projection: 160 pair tiles on 74 SM pairs = 2 waves + 12 -> narrow tail tiles
+    assert plan(8192, 1280, 5120) == (256, 1, 128)
+    assert plan(8192, 1280, 1280) == (256, 1, 128)
+    # level-1 MLP GEMM1: 640 tiles = 8 waves + 48: a tail wave would not be shorter -> none
+    assert plan(8192, 5120, 1280) == (256, 1, 0)
+    # QKV projection: 480 tiles = 6 waves + 36 -> 72 half-width tiles
+    assert plan(8192, 3840, 1280) == (256, 1, 128)
+    # a single 128-row tile stays on the 1-SM kernel
+    bn, two, tail = plan(64, 1280, 1280)
+    assert two == 0 and tail == 0 and bn in (64, 128, 256)
+    # every answer is a legal configuration, on any SM count
+    for sms in (148, 132, 74):
+        for m, n, k in [(8192, 1280, 5120), (300, 640, 64), (32768, 2560, 640), (2048, 1280, 1280), (12032, 512, 256)]:
+            bn, two, tail = plan(m, n, k, sms)
+            assert bn in (64, 128, 256) and two in (0, 1) and tail in (0, 64, 128)
+            assert tail == 0 or (two == 1 and bn == 256)
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "paella_b200")
     for dirpath, _, files in os.walk(pkg):
