@@ -4,14 +4,19 @@
 // ConvTranspose2d(k=2,s=2) in ref/src/modules.py (ResBlock :49-55, AttnBlock :71-74, embedding :130-134,
 // resamplers :153-156,172-175, clf/out_mapper :179-187) and ref/src/vqgan.py (ResBlock :16-20).
 //
-// Structure (one persistent CTA per SM, 192 threads):
-//   warp 0   : TMA producer  — cp.async.bulk.tensor 2D loads of 128x64 (A) and BLOCK_Nx64 (W) fp16 tiles,
-//              128B-swizzled, into a STAGES-deep shared-memory ring guarded by full/empty mbarriers
-//   warp 1   : MMA issuer    — one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per stage into one of
-//              two TMEM accumulator buffers; tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2-5: epilogue      — tcgen05.ld 32x32b (thread = row, registers = columns), fused bias / GELU+GRN
-//              statistics / residual+FiLM / un-patchify scatter / NCHW transpose, vectorised global stores;
-//              overlaps with the next tile's MMAs through the second TMEM buffer.
+// Two persistent, warp-specialised kernels share the epilogues:
+//   gemm_f16_cg2_kernel   2-SM tiles (cluster of 2, tcgen05.mma.cta_group::2, M256 x N{128,256}); the default for M > 128
+//   gemm_f16_kernel       1-SM tiles (M128 x N{64,128,256}); small M, and the im2col-free convolutions (AMODE 1/2)
+// Roles inside a CTA (64 + 32*E threads, E = 8 or 16 epilogue warps):
+//   warp 0   : TMA producer  - cp.async.bulk.tensor loads of the 128x64 A tile and of this CTA's share of the W tile,
+//              128B-swizzled, into a 4-8 stage shared-memory ring guarded by full/empty mbarriers
+//   warp 1   : MMA issuer    - one thread issues tcgen05.mma (K=16) x4 per stage into one of two TMEM accumulators;
+//              tcgen05.commit (multicast to both CTAs of a pair) releases the stage / publishes the accumulator
+//   warps 2+ : epilogue      - tcgen05.ld 32x32b (lane = row, registers = 32 columns), fused bias / GELU + GRN statistic /
+//              residual + FiLM / LayerNorm fold / un-patchify / NCHW transpose; the chunk is transposed inside the warp so
+//              that every store instruction writes whole 128-byte lines; overlaps the next tile's MMAs (second accumulator)
+// Scheduling: tile width from a tensor / L2-fabric cycle model (gemm_pick_block_n), narrow tail tiles for the leftover
+// of the last wave (gemm_tail_block_n), programmatic dependent launch so the prologue overlaps the previous kernel.
 #include "gemm.cuh"
 #include <type_traits>
 
