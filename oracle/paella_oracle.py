@@ -87,7 +87,7 @@ def r_embedding(r: Tensor, c_r: int, max_positions: int = 10000) -> Tensor:
     r = r * max_positions
     half = c_r // 2
     k = math.log(max_positions) / (half - 1)
-    freq = torch.exp(torch.arange(half, dtype=torch.float32) * (-k))
+    freq = torch.exp(torch.arange(half, dtype=torch.float32, device=r.device) * (-k))
     ang = r[:, None] * freq[None, :]
     emb = torch.cat([ang.sin(), ang.cos()], dim=1)
     if c_r % 2 == 1:
@@ -121,10 +121,10 @@ def dwconv3x3_nhwc(x: Tensor, w: Tensor, b: Tensor, x_skip: Optional[Tensor] = N
     p = k // 2
     src = x if x_skip is None else torch.cat([x, x_skip], dim=-1)
     srcp = F.pad(src, (0, 0, p, p, p, p))
-    out = torch.zeros(B, H, W, c, dtype=torch.float32) + b
+    out = torch.zeros(B, H, W, c, dtype=torch.float32, device=x.device) + b
     per = w.shape[1]
     for j in range(per):
-        chan = torch.arange(c) * per + j
+        chan = torch.arange(c, device=x.device) * per + j
         sj = srcp[..., chan]
         for ky in range(k):
             for kx in range(k):
@@ -177,7 +177,7 @@ def attention_core(q, k, v, nhead: int, attn_weights: Optional[Tensor] = None) -
     s = (qh @ kh.transpose(-2, -1)) / (hd ** 0.5)
     p = torch.softmax(s, dim=-1)
     if attn_weights is not None:
-        w = torch.ones(Nk)
+        w = torch.ones(Nk, device=q.device)
         w[-attn_weights.shape[0]:] = attn_weights.float()
         p = p * w
     o = p @ vh
@@ -339,7 +339,7 @@ def sample(sd, cfg: PaellaConfig, model_inputs: dict, latent_shape, unconditiona
     t_list = torch.linspace(t_start, t_end, steps + 1)
     temps = torch.linspace(temperature[0], temperature[1], steps)
     for i in range(steps):
-        t = torch.ones(B) * t_list[i]
+        t = torch.ones(B, device=sampled.device) * t_list[i]
         logits = paella_forward(sd, cfg, sampled, t, mm=mm, **model_inputs)
         if cfg_scale:
             logits = logits * cfg_scale + paella_forward(sd, cfg, sampled, t, mm=mm, **unconditional_inputs) * (1 - cfg_scale)
@@ -347,6 +347,6 @@ def sample(sd, cfg: PaellaConfig, model_inputs: dict, latent_shape, unconditiona
         p = scores.permute(0, 2, 3, 1).reshape(-1, logits.size(1))
         sampled = torch.argmax(p / draws["q"][i], dim=-1).view(logits.size(0), *logits.shape[2:])
         if i < renoise_steps:
-            t_next = torch.ones(B) * t_list[i + 1]
+            t_next = torch.ones(B, device=sampled.device) * t_list[i + 1]
             sampled, _ = add_noise(sampled, t_next, init_noise, draws["u"][i])
     return sampled
