@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PB200_ABI_VERSION 1
+#define PB200_ABI_VERSION 2
 
 const char* pb200_last_error(void);
 int pb200_abi_version(void);
@@ -102,8 +102,12 @@ enum pb200_epilogue {
     /* LayerNorm folded across two GEMMs (the AttnBlock's pre-norm, ref/src/modules.py:78): the producer also emits
      * the fp16 copy of its output row and the row statistics, the consumer multiplies the UN-normalised fp16 rows and
      * normalises in its epilogue:  LN(x) W^T = rstd * (x W^T - mean * rowsum(W)). */
-    PB200_EPI_RESID_LN_F32 = 6, /* RESID_F32 + out16[M,ldo] = fp16(out); ln_stat[row] += (sum out, sum out^2)  */
-    PB200_EPI_F16_LN = 7       /* out fp16 = rstd[row]*(acc - mean[row]*ln_wsum[n]) + bias, stats from ln_stat */
+    PB200_EPI_RESID_LN_F32 = 6, /* RESID_F32 + out16[M,ldo] = fp16(out - s); ln_stat[row] += (sum (out-s), sum (out-s)^2),
+                                 * s = ln_shift[row] (0 if NULL).  LayerNorm is invariant under a per-row shift, so any s
+                                 * is exact; an s near the row mean keeps the fp16 rounding of the copy relative to the row's
+                                 * SPREAD instead of its offset (the executor passes the mean the previous AttnBlock saw). */
+    PB200_EPI_F16_LN = 7       /* out fp16 = rstd[row]*(acc - mean'[row]*ln_wsum[n]) + bias, (mean', rstd) of the shifted
+                                 * rows from ln_stat; if ln_mean_out: ln_mean_out[row] = ln_shift[row] + mean' (true mean) */
 };
 
 typedef struct pb200_gemm_epilogue {
@@ -127,6 +131,8 @@ typedef struct pb200_gemm_epilogue {
                                   over the ln_c columns of a row, fixed point (integer atomics: order-independent) */
     const float* ln_wsum;      /* F16_LN: [N] row sums of the fp16 weight matrix */
     int ln_c;                  /* F16_LN: number of columns the statistics cover (= K of this GEMM) */
+    const float* ln_shift;     /* RESID_LN / F16_LN: fp32 [M] per-row shift the producer subtracted, or NULL (= 0) */
+    float* ln_mean_out;        /* F16_LN: fp32 [M] true row mean (shift + mean of the shifted row), or NULL */
 } pb200_gemm_epilogue;
 
 int pb200_gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t m, int64_t n, int64_t k,
@@ -293,6 +299,30 @@ int pb200_vqgan_encode(pb200_vqgan* m, const float* img, int batch, int img_h, i
  * scale_factor (latents_nchw != NULL) -> img fp32 NCHW [B,3,4h,4w]. */
 int pb200_vqgan_decode(pb200_vqgan* m, const int64_t* indices, const float* latents_nchw, int batch, int h, int w,
                        float* img, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* One codec ResBlock on its own (ref/src/vqgan.py:36-42) -- what `vqgan.ResBlock.forward` runs outside a VQModel; inside
+ * one, encode/decode run the same kernels from the plan.  x_nhwc fp32 [B,h,w,c] is updated in place; dw_w9 = the depthwise
+ * kernel as [9][c] fp32 (tap-major), w1 [4c,c] / w2 [c,4c] fp16 row-major, gammas_host = the 6 scalars (HOST memory). */
+int64_t pb200_vqgan_resblock_workspace_bytes(int batch, int h, int w, int c);
+int pb200_vqgan_resblock(float* x_nhwc, int batch, int h, int w, int c, const float* dw_w9, const float* dw_bias,
+                         const void* w1_f16, const float* b1, const void* w2_f16, const float* b2, const float* gammas_host,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Output forms of the decoder's last kernel (out_block: 1x1 conv + PixelShuffle, ref/src/vqgan.py:86-89), fused with what
+ * the reference's callers do next (ref/src_distributed/train.py:168-171 `decode_indices(x).clamp(0, 1)`, then
+ * torchvision.utils.save_image's `mul(255).add_(0.5).clamp_(0, 255).to(uint8)` on an HWC view):
+ *   PB200_IMG_F32_NCHW          fp32 [B,3,4h,4w], unclamped               == pb200_vqgan_decode
+ *   PB200_IMG_F32_NCHW_CLAMP01  fp32 [B,3,4h,4w], clamp(0,1)
+ *   PB200_IMG_U8_NHWC           uint8 [B,4h,4w,3] = trunc(clamp(v,0,1)*255 + 0.5)   */
+enum { PB200_IMG_F32_NCHW = 0, PB200_IMG_F32_NCHW_CLAMP01 = 1, PB200_IMG_U8_NHWC = 2 };
+int pb200_vqgan_decode_ex(pb200_vqgan* m, const int64_t* indices, const float* latents_nchw, int batch, int h, int w,
+                          void* img, int img_mode, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Re-read the host-mirrored scalars (the six ResBlock gammas, kernel arguments) from the bound weight blob.  Needed when
+ * the blob was filled by anything other than pb200_vqgan_load_param on this handle (NCCL broadcast, a packed file,
+ * cudaMemcpy).  bind_weights marks them stale and encode/decode refresh lazily (one stream synchronisation), so calling
+ * this is only required when the blob CONTENT changes under an already-bound pointer.  Synchronises `stream`. */
+int pb200_vqgan_sync_params(pb200_vqgan* m, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ class GemmEpilogue(ctypes.Structure):
         ("ldr", c_int64), ("alpha", c_float), ("sqsum", c_void_p), ("rows_per_sample", c_int), ("film", c_void_p),
         ("film_ld", c_int64), ("film_off", c_int64), ("remap_in", c_int), ("remap_out", c_int), ("up_h", c_int),
         ("up_w", c_int), ("up_cout", c_int), ("out16", c_void_p), ("ln_stat", c_void_p), ("ln_wsum", c_void_p),
-        ("ln_c", c_int),
+        ("ln_c", c_int), ("ln_shift", c_void_p), ("ln_mean_out", c_void_p),
     ]
 
 
@@ -111,7 +111,15 @@ SIGNATURES = {
                                    c_int64, c_void_p]),
     "pb200_vqgan_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int64,
                                    c_void_p]),
+    "pb200_vqgan_decode_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int64,
+                                      c_void_p]),
+    "pb200_vqgan_sync_params": (c_int, [c_void_p, c_void_p]),
+    "pb200_vqgan_resblock_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "pb200_vqgan_resblock": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, POINTER(c_float), c_void_p, c_int64, c_void_p]),
 }
+
+IMG_F32_NCHW, IMG_F32_NCHW_CLAMP01, IMG_U8_NHWC = range(3)
 
 _lib = None
 
@@ -133,7 +141,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(l, name)        # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if l.pb200_abi_version() != 1:
+        if l.pb200_abi_version() != 2:
             raise PaellaB200Error("libpaella_b200.so ABI version mismatch")
         _lib = l
     return _lib

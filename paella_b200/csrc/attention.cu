@@ -253,10 +253,9 @@ int launch_attention(const AttnParams& p, cudaStream_t st) {
     switch (hd) {
 #define PB_ATT_CASE(H)                                                                                              \
     case H: {                                                                                                       \
-        static bool attr = false;                                                                                   \
-        if (!attr) {                                                                                                \
+        static DeviceOnce attr;                                                                                   \
+        if (attr.first()) {                                                                                                \
             PB_CUDA(cudaFuncSetAttribute(attention_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            attr = true;                                                                                            \
         }                                                                                                           \
         attention_kernel<H><<<grid, 128, smem, st>>>(p);                                                            \
         break;                                                                                                      \

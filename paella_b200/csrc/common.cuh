@@ -47,8 +47,14 @@ const char* last_error();
 
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
-int sm_count();        // multiprocessor count of the current device (cached)
+int sm_count();        // multiprocessor count of the CURRENT device (cached per device)
 int max_threads_per_sm();
+// One-time per-DEVICE setup (cudaFuncSetAttribute is a per-device property): true the first time it is called with this
+// flag word while device d is current.  `static DeviceOnce once; if (once.first()) { ... }`
+struct DeviceOnce {
+    unsigned long long mask = 0;      // guarded by a library-wide mutex in first()
+    bool first();
+};
 
 // ---------------------------------------------------------------- measurement hooks (bench.py)
 void prof_count_launch();            // every kernel launch of the library bumps one counter

@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include "paella_b200.h"
 
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges cost ~nothing unless a tool (nsys / ncu --nvtx) is attached
+
 #include <atomic>
 #include <cstring>
 #include <map>
@@ -16,22 +18,43 @@ static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error() { return g_err.c_str(); }
 
-static int g_sm = -1, g_tpsm = -1;
-static void query_device() {
-    if (g_sm >= 0) return;
+// per-device caches (a process may drive several GPUs: Paella on cuda:0, VQModel on cuda:1)
+constexpr int kMaxDev = 64;
+static int g_sm[kMaxDev], g_tpsm[kMaxDev];
+static bool g_dev_known[kMaxDev];
+static std::mutex g_dev_mu;
+static int current_device() {
     int dev = 0;
-    cudaDeviceProp p;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
-        g_sm = p.multiProcessorCount;
-        g_tpsm = p.maxThreadsPerMultiProcessor;
-    } else {
-        (void)cudaGetLastError();
-        g_sm = 0;
-        g_tpsm = 2048;
-    }
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    return dev;
 }
-int sm_count() { query_device(); return g_sm; }
-int max_threads_per_sm() { query_device(); return g_tpsm; }
+static int query_device() {
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDev) return -1;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (!g_dev_known[dev]) {
+        int sm = 0, tpsm = 2048;
+        if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&tpsm, cudaDevAttrMaxThreadsPerMultiProcessor, dev) != cudaSuccess) {
+            (void)cudaGetLastError();
+            sm = 0; tpsm = 2048;
+        }
+        g_sm[dev] = sm; g_tpsm[dev] = tpsm; g_dev_known[dev] = true;
+    }
+    return dev;
+}
+int sm_count() { const int d = query_device(); return d < 0 ? 0 : g_sm[d]; }
+int max_threads_per_sm() { const int d = query_device(); return d < 0 ? 2048 : g_tpsm[d]; }
+
+bool DeviceOnce::first() {
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDev) return true;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    const unsigned long long bit = 1ull << dev;
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
 
 // ------------------------------------------------------------------ measurement hooks
 static std::atomic<long long> g_launches{0};
@@ -47,7 +70,11 @@ static std::mutex g_prof_mu;
 void prof_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 bool prof_enabled() { return g_prof; }
 
+// Every kernel family launched by the library sits inside an NVTX range named after it ("gemm_gelu", "attention",
+// "dwconv_ln", "fused_sampler", "vq_nearest", ...): `ncu --nvtx --nvtx-include "attention/"` or an nsys timeline can
+// select a family without knowing mangled kernel names.
 ProfScope::ProfScope(const char* tag, double work, cudaStream_t s) : slot(-1), st(s) {
+    nvtxRangePushA(tag);
     if (!g_prof) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     ProfRec r;
@@ -59,6 +86,7 @@ ProfScope::ProfScope(const char* tag, double work, cudaStream_t s) : slot(-1), s
     g_recs.push_back(r);
 }
 ProfScope::~ProfScope() {
+    nvtxRangePop();
     if (slot < 0) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     cudaEventRecord(g_recs[slot].e1, st);

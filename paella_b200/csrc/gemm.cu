@@ -105,6 +105,7 @@ template <>
 struct EpiPre<PB200_EPI_RESID_LN_F32> {
     float4 r[8];
     float ln_s = 0.f, ln_q = 0.f;      // this lane's row: sum / sum of squares over the chunks of the tile done so far
+    float shift = 0.f;                 // this lane's row: the shift subtracted before the fp16 copy and the statistics
 };
 
 // Coalescing.  tcgen05.ld hands every lane one ROW of the chunk (32 consecutive columns), so a direct 16-byte store
@@ -178,7 +179,12 @@ __device__ __forceinline__ void epilogue_preload(const pb200_gemm_epilogue& ep, 
             const float ex2 = (float)st.y * (1.0f / 65536.0f) * inv_c;
             pre.neg_mean = -mean;
             pre.rstd = 1.0f / sqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-6f);
+            // the true row mean, for the next producer's shift (every N-tile writes the same value: benign)
+            if (ep.ln_mean_out) ep.ln_mean_out[row] = (ep.ln_shift ? ep.ln_shift[row] : 0.f) + mean;
         }
+    }
+    if constexpr (MODE == PB200_EPI_RESID_LN_F32) {
+        if (first_chunk) pre.shift = (ep.ln_shift && row < M) ? ep.ln_shift[row] : 0.f;
     }
     if constexpr (MODE == PB200_EPI_RESID_F32 || MODE == PB200_EPI_RESID_LN_F32) {
         const int col = col0 + (lane & 7) * 4;       // transposed layout: item i = row of lane (lane & 24) + i
@@ -318,10 +324,13 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
         transpose8x8_f4(v, lane);
         const int col = col0 + (lane & 7) * 4;
         float* obase = reinterpret_cast<float*>(ep.out);
-        float ls[8], lq[8];
+        float ls[8], lq[8], sh[8];
         if constexpr (MODE == PB200_EPI_RESID_LN_F32) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ls[i] = lq[i] = 0.f;
+            for (int i = 0; i < 8; ++i) {
+                ls[i] = lq[i] = 0.f;
+                sh[i] = __shfl_sync(0xffffffffu, pre.shift, (lane & 24) + i);     // item i = the row of lane (lane & 24) + i
+            }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -341,6 +350,7 @@ __device__ __forceinline__ void epilogue_chunk(const pb200_gemm_epilogue& ep, in
                 }
                 *reinterpret_cast<float4*>(obase + (int64_t)r * ep.ldo + col) = y;
                 if constexpr (MODE == PB200_EPI_RESID_LN_F32) {
+                    y.x -= sh[i]; y.y -= sh[i]; y.z -= sh[i]; y.w -= sh[i];      // (after the fp32 store of the true value)
                     uint2 pk;
                     pk.x = pack_half2(y.x, y.y);
                     pk.y = pack_half2(y.z, y.w);
@@ -795,10 +805,9 @@ static int launch_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
                       const pb200_gemm_epilogue& ep, int M, int N, int K, cudaStream_t st) {
     constexpr int STAGES = BLOCK_N >= 256 ? 6 : 8;
     constexpr int SMEM = STAGES * (GEMM_BLOCK_M * 128 + (BLOCK_N / 2) * 128) + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         PB_CUDA(cudaFuncSetAttribute(gemm_f16_cg2_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
     }
     const int n_big = ceil_div(M, 2 * GEMM_BLOCK_M) * ceil_div(N, BLOCK_N);
     const int max_pairs = sm_count() / 2;
@@ -849,11 +858,10 @@ template <int BLOCK_N, int MODE, int AMODE = 0>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const pb200_gemm_epilogue& ep, int M, int N, int K,
                       cudaStream_t st, const ConvGeom* geom = nullptr) {
     using L = GemmSmem<BLOCK_N>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         PB_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BLOCK_N, MODE, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      L::SMEM_BYTES));
-        attr_set = true;
     }
     ConvGeom g;
     memset(&g, 0, sizeof(g));

@@ -70,7 +70,7 @@ int launch_embed_tokens(const int64_t* tokens, const float* emb, int num_labels,
 template <bool PATCHIFY>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, int64_t rows, int C, float scale,
                                                       float shift, __half* __restrict__ out16, float* __restrict__ out32,
-                                                      int h, int w) {
+                                                      int h, int w, float* __restrict__ mean_out) {
     pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
     float s = 0.f;
     for (int i = lane; i < nv; i += 32) { const float4 v = xr[i]; s += (v.x + v.y) + (v.z + v.w); }
     const float mean = warp_sum(s) / C;
+    if (mean_out && lane == 0) mean_out[row] = mean;
     float q = 0.f;
     for (int i = lane; i < nv; i += 32) {
         const float4 v = xr[i];
@@ -111,12 +112,12 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
 }
 
 int launch_ln_rows(const float* x, int64_t rows, int C, float scale, float shift, __half* out16, float* out32,
-                   cudaStream_t st) {
+                   cudaStream_t st, float* mean_out) {
     ProfScope prof("layernorm", (double)rows * C * (out16 ? 6.0 : 8.0), st);
     PB_CHECK(C % 4 == 0, "layernorm: C=%d must be a multiple of 4", C);
     PB_CHECK((out16 != nullptr) != (out32 != nullptr), "layernorm: exactly one output");
     if (rows == 0) return 0;
-    ln_rows_kernel<false><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, C, scale, shift, out16, out32, 0, 0);
+    ln_rows_kernel<false><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, C, scale, shift, out16, out32, 0, 0, mean_out);
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -125,7 +126,7 @@ int launch_ln_patchify2(const float* x, int B, int h, int w, int c, __half* out,
     ProfScope prof("layernorm", (double)B * h * w * c * 6.0, st);
     PB_CHECK(c % 4 == 0 && h % 2 == 0 && w % 2 == 0, "ln_patchify: bad geometry %dx%dx%d", h, w, c);
     const int64_t rows = (int64_t)B * h * w;
-    ln_rows_kernel<true><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, c, 1.0f, 0.0f, out, nullptr, h, w);
+    ln_rows_kernel<true><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, c, 1.0f, 0.0f, out, nullptr, h, w, nullptr);
     PB_LAUNCH_CHECK();
     return 0;
 }

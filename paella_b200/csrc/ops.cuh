@@ -10,9 +10,9 @@ int launch_embed_tokens(const int64_t* tokens, const float* emb, int num_labels,
                         __half* out, cudaStream_t st);
 
 // LayerNorm over the last dim (eps 1e-6, no affine), optional scalar affine y*scale+shift, fp32 in.
-// Exactly one of out16 / out32 is non-null.  rows x C, C % 4 == 0.
+// Exactly one of out16 / out32 is non-null.  rows x C, C % 4 == 0.  mean_out (optional): fp32 [rows] row means.
 int launch_ln_rows(const float* x, int64_t rows, int C, float scale, float shift, __half* out16, float* out32,
-                   cudaStream_t st);
+                   cudaStream_t st, float* mean_out = nullptr);
 
 // LN2d + 2x2 patchify: x fp32 [B,h,w,c] -> fp16 [B*(h/2)*(w/2), 4c] with column = (dy*2+dx)*c + ch
 int launch_ln_patchify2(const float* x, int B, int h, int w, int c, __half* out, cudaStream_t st);

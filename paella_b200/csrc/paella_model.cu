@@ -103,6 +103,8 @@ struct BlockPlan {
     int64_t inproj_wsum = -1;       // ATTN: row sums of in_proj_weight (LayerNorm folded into the QKV GEMM)
     int attn_index = -1;
     int ln_fold_attn = -1;          // RES/FF: index of the AttnBlock that directly consumes this block's output, or -1
+    int ln_shift_attn = -1;         // RES/FF (folded) and ATTN: index of the previous AttnBlock on the same residual stream,
+                                    // whose input row means are the per-row shift of the folded LayerNorm; -1 = none
     int64_t rs_w = -1, rs_b = -1;
 };
 
@@ -326,14 +328,33 @@ static int build_plan(pb200_paella* m) {
             t.film_fused = true;
         }
     }
+    // Each AttnBlock's predecessor on the same residual stream (same level, no resampler in between; the deepest level's
+    // SAVE is a no-op on the tensor): the row means that block saw are the shift of this block's folded LayerNorm.
+    {
+        int prev = -1, prev_level = -1;
+        for (BlockPlan& b : m->blocks) {
+            if (b.kind == BK_DOWN || b.kind == BK_UP || (b.kind == BK_SAVE && b.level != L - 1)) prev = -1;
+            if (b.kind == BK_ATTN) {
+                b.ln_shift_attn = (prev >= 0 && prev_level == b.level) ? prev : -1;
+                prev = b.attn_index;
+                prev_level = b.level;
+            }
+        }
+    }
+    // The LayerNorm fold rounds the producer's rows to fp16 before the mean is removed; it is only used where a shift close
+    // to the row mean is available (every AttnBlock but the first of a stream segment), which keeps that rounding relative
+    // to the row's spread (tests/test_oracle_lnfold.py; DESIGN.md "Numerics").
     static const bool no_fold = getenv("PB200_NO_LN_FOLD") != nullptr;      // A/B knob
     for (size_t i = 0; !no_fold && i + 1 < m->blocks.size(); ++i) {
         BlockPlan& a = m->blocks[i];
         if (a.kind != BK_RES && a.kind != BK_FF) continue;
         size_t j = i + 1;
         if (m->blocks[j].kind == BK_TIME && m->blocks[j].film_fused) ++j;
-        if (j < m->blocks.size() && m->blocks[j].kind == BK_ATTN && m->blocks[j].level == a.level)
+        if (j < m->blocks.size() && m->blocks[j].kind == BK_ATTN && m->blocks[j].level == a.level &&
+            m->blocks[j].ln_shift_attn >= 0) {
             a.ln_fold_attn = m->blocks[j].attn_index;
+            a.ln_shift_attn = m->blocks[j].ln_shift_attn;
+        }
     }
     return 0;
 }
@@ -357,6 +378,8 @@ struct FeatWs {
     uint64_t *gsq, *gscale;      // GRN statistic ping/pong (2^-24 fixed point)
     int64_t* lnstat;             // folded LayerNorm: per AttnBlock [M][2] fixed-point row statistics
     int64_t lnstat_stride;       // int64 elements per AttnBlock
+    float* lnmean;               // per AttnBlock [M]: mean of its input rows (the next folded LayerNorm's per-row shift)
+    int64_t lnmean_stride;
     float *r_emb, *film, *y;
 };
 
@@ -383,6 +406,8 @@ static void plan_features(const pb200_paella* m, int Bt, int H, int W, Arena& ar
             if (b.kind == BK_ATTN) { const int64_t M = (int64_t)Bt * (P >> (2 * b.level)); max_m = M > max_m ? M : max_m; }
         ws.lnstat_stride = 2 * max_m;
         ws.lnstat = ar.take<int64_t>(ws.lnstat_stride * (m->n_attn > 0 ? m->n_attn : 1));
+        ws.lnmean_stride = max_m;
+        ws.lnmean = ar.take<float>(ws.lnmean_stride * (m->n_attn > 0 ? m->n_attn : 1));
     }
     ws.r_emb = ar.take<float>((int64_t)Bt * c.c_r);
     ws.film = ar.take<float>((int64_t)Bt * (m->film_total > 0 ? m->film_total : 4));
@@ -701,6 +726,7 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
                 if (fold) {
                     e2.out16 = ws.a16;
                     e2.ln_stat = ws.lnstat + ws.lnstat_stride * b.ln_fold_attn;
+                    e2.ln_shift = ws.lnmean + ws.lnmean_stride * b.ln_shift_attn;
                     ln_ready = b.ln_fold_attn;
                 }
                 PB_TRY(m->gemm(ws.h16, 4 * (int64_t)ch, M, 4 * (int64_t)ch, b.w2, ch, e2, st));
@@ -712,12 +738,15 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
             case BK_ATTN: {
                 const bool folded = ln_ready == b.attn_index;
                 pb200_gemm_epilogue e1 = epi(folded ? PB200_EPI_F16_LN : PB200_EPI_F16, m->w<float>(b.inproj_b), ws.qkv16, 3 * ch);
-                if (folded) {       // a16 = fp16(x) and the row statistics came out of the previous GEMM's epilogue
+                float* mean_out = ws.lnmean + ws.lnmean_stride * b.attn_index;      // read by the next block's folded LayerNorm
+                if (folded) {       // a16 = fp16(x - shift) and the row statistics came out of the previous GEMM's epilogue
                     e1.ln_stat = ws.lnstat + ws.lnstat_stride * b.attn_index;
                     e1.ln_wsum = m->w<float>(b.inproj_wsum);
                     e1.ln_c = ch;
+                    e1.ln_shift = ws.lnmean + ws.lnmean_stride * b.ln_shift_attn;
+                    e1.ln_mean_out = mean_out;
                 } else {
-                    PB_TRY(launch_ln_rows(x, M, ch, 1.0f, 0.0f, ws.a16, nullptr, st));
+                    PB_TRY(launch_ln_rows(x, M, ch, 1.0f, 0.0f, ws.a16, nullptr, st, mean_out));
                 }
                 PB_TRY(m->gemm(ws.a16, ch, M, ch, b.inproj_w, 3 * (int64_t)ch, e1, st));
                 AttnParams ap;

@@ -384,11 +384,10 @@ int launch_fused_sampler(const __half* a16, int64_t R, int Kc, const __half* w16
             const int rs = (int)(rng.stride / NL);
             const int n_blocks = (int)((R + 4 * (int64_t)rs - 1) / (4 * (int64_t)rs));
             const int tpb = (rs + SH_JJ - 1) / SH_JJ;
-            static bool attr2 = false;
-            if (!attr2) {
+            static DeviceOnce attr2;
+            if (attr2.first()) {
                 PB_CUDA(cudaFuncSetAttribute(fused_sampler_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM));
-                attr2 = true;
-            }
+    }
             ProfScope prof("fused_sampler", 2.0 * (double)R * (double)NL * (double)Kc, st);
             CUtensorMap tf, tw;
             const int64_t dims[4] = {Kc, 4, rs, n_blocks};
@@ -401,10 +400,9 @@ int launch_fused_sampler(const __half* a16, int64_t R, int Kc, const __half* w16
             return 0;
         }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         PB_CUDA(cudaFuncSetAttribute(fused_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMP_SMEM));
-        attr_set = true;
     }
     ProfScope prof("fused_sampler", 2.0 * (double)R * (double)NL * (double)Kc, st);
     CUtensorMap ta, tw;

@@ -85,10 +85,13 @@ __global__ void __launch_bounds__(256) vq_in_block_kernel(const float* __restric
     *reinterpret_cast<float4*>(out + pos * c0 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
-// out_block: Conv2d(c0 -> 12, k=1) + PixelShuffle(2).  x NHWC fp32 [B,h2,w2,c0] -> img NCHW [B,3,2h2,2w2]; warp per position
+// out_block: Conv2d(c0 -> 12, k=1) + PixelShuffle(2).  x NHWC fp32 [B,h2,w2,c0] -> img NCHW [B,3,2h2,2w2]; warp per position.
+// MODE (include/paella_b200.h PB200_IMG_*): 0 raw fp32 NCHW, 1 clamp(0,1) fp32 NCHW, 2 uint8 NHWC [B,2h2,2w2,3] with
+// save_image's rounding -- the callers' clamp / byte conversion passes fused into the store.
+template <int MODE>
 __global__ void __launch_bounds__(256) vq_out_block_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, int B, int h2, int w2, int c0,
-                                                           float* __restrict__ img) {
+                                                           void* __restrict__ img_out) {
     const int lane = threadIdx.x & 31;
     const int64_t pos = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (pos >= (int64_t)B * h2 * w2) return;
@@ -110,7 +113,16 @@ __global__ void __launch_bounds__(256) vq_out_block_kernel(const float* __restri
         const int rem = (int)(pos - (int64_t)b * h2 * w2);
         const int y = rem / w2, xx = rem - y * w2;
         const int c = lane >> 2, d = lane & 3;
-        img[(((int64_t)b * 3 + c) * (2 * h2) + 2 * y + (d >> 1)) * (2 * w2) + 2 * xx + (d & 1)] = v + bias[lane];
+        v += bias[lane];
+        if (MODE != 0) v = fminf(fmaxf(v, 0.f), 1.f);
+        if (MODE == 2) {
+            uint8_t* img = reinterpret_cast<uint8_t*>(img_out);
+            img[(((int64_t)b * (2 * h2) + 2 * y + (d >> 1)) * (2 * w2) + 2 * xx + (d & 1)) * 3 + c] =
+                (uint8_t)fminf(v * 255.0f + 0.5f, 255.0f);
+        } else {
+            float* img = reinterpret_cast<float*>(img_out);
+            img[(((int64_t)b * 3 + c) * (2 * h2) + 2 * y + (d >> 1)) * (2 * w2) + 2 * xx + (d & 1)] = v;
+        }
     }
 }
 
@@ -226,6 +238,7 @@ struct pb200_vqgan {
     int cpad0, cpad1;
     VqResBlock enc0, enc1, dec_last;
     std::vector<VqResBlock> bottleneck;
+    bool host_params_stale = true;                 // the gammas' host mirror has not been read from the bound blob yet
     std::map<std::tuple<const void*, int64_t, int64_t, int64_t, int>, CUtensorMap> tmaps;
 
     int64_t add(const std::string& name, int64_t numel, int kind, int64_t dst_numel, int eb, int d0 = 0, int d1 = 0, int d2 = 0,
@@ -310,18 +323,25 @@ static void vq_plan(const pb200_vqgan* m, int B, int H, int W, uint8_t* base, in
     ws.idx = (int64_t*)take(M1 * 8);
 }
 
+// The part of a codec ResBlock (ref/src/vqgan.py:36-42) before its MLP: x += g2 * dw3x3(pad(LN(x)(1+g0)+g1)), then
+// a16 = fp16(LN(x)(1+g3)+g4).  x: NHWC fp32 [B,h,w,c], updated in place.
+static int resblock_front(float* x, int B, int h, int w, int c, const float* dw_w9, const float* dw_b, const float* gam,
+                          float* tmp32, __half* a16, cudaStream_t st) {
+    const int64_t M = (int64_t)B * h * w;
+    PB_TRY(launch_ln_rows(x, M, c, 1.0f + gam[0], gam[1], nullptr, tmp32, st));
+    {
+        ProfScope prof("vq_dwconv", (double)M * c * 12.0, st);
+        vq_dw_residual_kernel<<<ceil_div(M * (c / 4), 256), 256, 0, st>>>(tmp32, x, dw_w9, dw_b, gam[2], B, h, w, c);
+        PB_LAUNCH_CHECK();
+    }
+    return launch_ln_rows(x, M, c, 1.0f + gam[3], gam[4], a16, nullptr, st);
+}
+
 // x: NHWC fp32 [B,h,w,c], updated in place (ref/src/vqgan.py:36-42)
 static int run_resblock(pb200_vqgan* m, const VqResBlock& rb, float* x, int B, int h, int w, VqWs& ws, cudaStream_t st) {
     const int c = rb.c;
     const int64_t M = (int64_t)B * h * w;
-    PB_TRY(launch_ln_rows(x, M, c, 1.0f + rb.gam[0], rb.gam[1], nullptr, ws.tmp32, st));
-    {
-        ProfScope prof("vq_dwconv", (double)M * c * 12.0, st);
-        vq_dw_residual_kernel<<<ceil_div(M * (c / 4), 256), 256, 0, st>>>(ws.tmp32, x, m->w<float>(rb.dw_w), m->w<float>(rb.dw_b),
-                                                                         rb.gam[2], B, h, w, c);
-        PB_LAUNCH_CHECK();
-    }
-    PB_TRY(launch_ln_rows(x, M, c, 1.0f + rb.gam[3], rb.gam[4], ws.a16, nullptr, st));
+    PB_TRY(resblock_front(x, B, h, w, c, m->w<float>(rb.dw_w), m->w<float>(rb.dw_b), rb.gam, ws.tmp32, ws.a16, st));
     pb200_gemm_epilogue e1 = vepi(PB200_EPI_GELU_F16, m->w<float>(rb.b1), ws.h16, 4 * c);
     PB_TRY(m->gemm(ws.a16, c, M, c, rb.w1, 4 * (int64_t)c, e1, st));
     pb200_gemm_epilogue e2 = vepi(PB200_EPI_RESID_F32, m->w<float>(rb.b2), x, c);
@@ -339,6 +359,35 @@ static void conv_tile(int gw, int& tw, int& th) {
 }  // namespace pb
 
 extern "C" {
+
+int64_t pb200_vqgan_resblock_workspace_bytes(int batch, int h, int w, int c) {
+    const int64_t M = (int64_t)batch * h * w;
+    auto up = [](int64_t b) { return (b + 255) / 256 * 256; };
+    return up(M * c * 4) + up(M * c * 2) + up(M * 4 * c * 2) + 256;
+}
+
+int pb200_vqgan_resblock(float* x_nhwc, int batch, int h, int w, int c, const float* dw_w9, const float* dw_bias, const void* w1_f16,
+                         const float* b1, const void* w2_f16, const float* b2, const float* gammas_host, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+    PB_CHECK(x_nhwc && dw_w9 && dw_bias && w1_f16 && b1 && w2_f16 && b2 && gammas_host, "vqgan_resblock: null pointer");
+    PB_CHECK(c % 8 == 0, "vqgan_resblock: c=%d must be a multiple of 8", c);
+    PB_CHECK(((uintptr_t)workspace & 255) == 0 && workspace_bytes >= pb200_vqgan_resblock_workspace_bytes(batch, h, w, c),
+             "vqgan_resblock: workspace too small or misaligned");
+    if (batch == 0 || h == 0 || w == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t M = (int64_t)batch * h * w;
+    auto up = [](int64_t b) { return (b + 255) / 256 * 256; };
+    uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+    float* tmp32 = reinterpret_cast<float*>(base);
+    __half* a16 = reinterpret_cast<__half*>(base + up(M * c * 4));
+    __half* h16 = reinterpret_cast<__half*>(base + up(M * c * 4) + up(M * c * 2));
+    PB_TRY(resblock_front(x_nhwc, batch, h, w, c, dw_w9, dw_bias, gammas_host, tmp32, a16, st));
+    pb200_gemm_epilogue e1 = vepi(PB200_EPI_GELU_F16, b1, h16, 4 * c);
+    PB_TRY(gemm_f16(a16, c, w1_f16, c, M, 4 * (int64_t)c, c, e1, st));
+    pb200_gemm_epilogue e2 = vepi(PB200_EPI_RESID_F32, b2, x_nhwc, c);
+    e2.resid = x_nhwc; e2.ldr = c; e2.alpha = gammas_host[5];
+    return gemm_f16(h16, 4 * (int64_t)c, w2_f16, 4 * (int64_t)c, M, c, 4 * (int64_t)c, e2, st);
+}
 
 int pb200_vqgan_create(const pb200_vqgan_config* cfg, pb200_vqgan** out) {
     PB_CHECK(cfg && out, "vqgan_create: null argument");
@@ -385,6 +434,18 @@ int pb200_vqgan_bind_weights(pb200_vqgan* m, void* blob) {
     PB_CHECK(((uintptr_t)blob & 255) == 0, "weight blob must be 256-byte aligned");
     m->blob = reinterpret_cast<uint8_t*>(blob);
     m->tmaps.clear();
+    m->host_params_stale = true;
+    return 0;
+}
+
+int pb200_vqgan_sync_params(pb200_vqgan* m, void* stream) {
+    PB_CHECK(m->blob != nullptr, "sync_params: bind a weight blob first");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (const VqParam& p : m->params)
+        if (p.host_copy)
+            PB_CUDA(cudaMemcpyAsync(p.host_copy, m->blob + p.dst_off, p.numel * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    m->host_params_stale = false;
     return 0;
 }
 int pb200_vqgan_num_params(const pb200_vqgan* m) { return (int)m->params.size(); }
@@ -404,10 +465,7 @@ int pb200_vqgan_load_param(pb200_vqgan* m, const char* name, const float* src, i
     cudaStream_t st = (cudaStream_t)stream;
     vq_pack_kernel<<<ceil_div(p.dst_numel, 256), 256, 0, st>>>(src, m->blob + p.dst_off, p.kind, p.dst_numel, p.d0, p.d1, p.d2);
     PB_LAUNCH_CHECK();
-    if (p.host_copy) {      // the 6 ResBlock gammas are kernel arguments
-        PB_CUDA(cudaMemcpyAsync(p.host_copy, src, p.numel * sizeof(float), cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaStreamSynchronize(st));
-    }
+    if (p.host_copy) m->host_params_stale = true;      // the 6 ResBlock gammas are kernel arguments: re-read lazily
     return 0;
 }
 
@@ -421,6 +479,7 @@ int64_t pb200_vqgan_workspace_bytes(const pb200_vqgan* m, int batch, int img_h, 
 int pb200_vqgan_encode(pb200_vqgan* m, const float* img, int batch, int img_h, int img_w, float* latents_nchw,
                        float* quantised_nchw, int64_t* indices, void* workspace, int64_t workspace_bytes, void* stream) {
     PB_CHECK(m->blob != nullptr, "encode: weights not bound");
+    if (m->host_params_stale) PB_TRY(pb200_vqgan_sync_params(m, stream));
     PB_CHECK(img_h % 4 == 0 && img_w % 4 == 0, "encode: image %dx%d not divisible by 4", img_h, img_w);
     PB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -480,7 +539,14 @@ int pb200_vqgan_encode(pb200_vqgan* m, const float* img, int batch, int img_h, i
 
 int pb200_vqgan_decode(pb200_vqgan* m, const int64_t* indices, const float* latents_nchw, int batch, int h, int w, float* img,
                        void* workspace, int64_t workspace_bytes, void* stream) {
+    return pb200_vqgan_decode_ex(m, indices, latents_nchw, batch, h, w, img, PB200_IMG_F32_NCHW, workspace, workspace_bytes, stream);
+}
+
+int pb200_vqgan_decode_ex(pb200_vqgan* m, const int64_t* indices, const float* latents_nchw, int batch, int h, int w, void* img,
+                          int img_mode, void* workspace, int64_t workspace_bytes, void* stream) {
     PB_CHECK(m->blob != nullptr, "decode: weights not bound");
+    PB_CHECK(img_mode >= 0 && img_mode <= 2, "decode: unknown image mode %d", img_mode);
+    if (m->host_params_stale) PB_TRY(pb200_vqgan_sync_params(m, stream));
     PB_CHECK((indices != nullptr) != (latents_nchw != nullptr), "decode: pass indices or latents, not both");
     PB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -529,7 +595,10 @@ int pb200_vqgan_decode(pb200_vqgan* m, const int64_t* indices, const float* late
     PB_TRY(run_resblock(m, m->dec_last, ws.xa, B, h0, w0, ws, st));
     {
         ProfScope prof("vq_out_block", (double)M0 * (c0 * 4.0 + 48.0), st);
-        vq_out_block_kernel<<<ceil_div(M0, 8), 256, 0, st>>>(ws.xa, m->w<float>(m->out_w), m->w<float>(m->out_b), B, h0, w0, c0, img);
+        const float *ow = m->w<float>(m->out_w), *ob = m->w<float>(m->out_b);
+        if (img_mode == PB200_IMG_U8_NHWC) vq_out_block_kernel<2><<<ceil_div(M0, 8), 256, 0, st>>>(ws.xa, ow, ob, B, h0, w0, c0, img);
+        else if (img_mode == PB200_IMG_F32_NCHW_CLAMP01) vq_out_block_kernel<1><<<ceil_div(M0, 8), 256, 0, st>>>(ws.xa, ow, ob, B, h0, w0, c0, img);
+        else vq_out_block_kernel<0><<<ceil_div(M0, 8), 256, 0, st>>>(ws.xa, ow, ob, B, h0, w0, c0, img);
         PB_LAUNCH_CHECK();
     }
     return 0;

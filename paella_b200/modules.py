@@ -370,7 +370,8 @@ class Paella(nn.Module):
             pass
 
     def _device(self):
-        return self.in_mapper[0].weight.device
+        po = getattr(self, "_packed_only", None)
+        return po if po is not None else self.in_mapper[0].weight.device
 
     def _weights_key(self):
         return (str(self._device()),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -417,18 +418,64 @@ class Paella(nn.Module):
                           f"pb200_paella_load_param({name.decode()})")
                 torch.cuda.current_stream().synchronize()     # temporaries from .float() must outlive the copies
             if distributed:
-                dist.broadcast(self._blob, src=broadcast_src)
+                from .parallel import broadcast_blob
+                broadcast_blob(self._blob, src=broadcast_src)      # + checksum agreement across ranks (raises on mismatch)
         self._packed_key = self._weights_key()
         self._cond_single = None
         return self
 
     def _ensure_packed(self):
+        if getattr(self, "_packed_only", None) is not None:
+            return          # from_packed(): the blob IS the model; the nn parameters are meta placeholders
         if self._handle is None or self._packed_key != self._weights_key():
             self.pack_weights()
 
     def _apply(self, fn, *a, **k):      # .to()/.cuda()/.half(): repack lazily
+        if getattr(self, "_packed_only", None) is not None:
+            return self     # a packed-only model lives where from_packed() put it
         self._packed_key = None
         return super()._apply(fn, *a, **k)
+
+    # -------------------------------------------------------------- on-disk packed form
+    def save_packed(self, path: str):
+        """Write the library's packed weight blob (fp16 GEMM weights, repacked conv kernels, fused FiLM table, derived
+        row sums) + the constructor config to ``path``: what ``tools/pack_checkpoint.py`` produces from ``paella_v3.pt``
+        (nb:178-180).  ``Paella.from_packed`` memory-maps nothing and converts nothing: one H2D copy of 2.0 GB instead of
+        materialising 4.0 GB of fp32 parameters and running the pack kernels."""
+        from .packed import save_blob
+        self._ensure_packed()
+        save_blob(path, "paella", dict(self._cfg, dropout=0.0), self._blob)
+
+    @classmethod
+    def from_packed(cls, path: str, device="cuda"):
+        from .packed import load_blob
+        cfg, blob = load_blob(path, "paella", device)
+        with torch.device("meta"):
+            m = cls(**cfg)
+        m.eval().requires_grad_(False)
+        L = lib()
+        m._packed_only = torch.device(device) if not isinstance(device, torch.device) else device
+        if m._packed_only.index is None:
+            m._packed_only = torch.device("cuda", torch.cuda.current_device())
+        c = m._cfg
+        ccfg = _lib.PaellaConfig()
+        for k in ("c_in", "c_out", "num_labels", "c_r", "patch_size", "c_cond", "clip_embd", "byt5_embd", "clip_seq_len", "kernel_size"):
+            setattr(ccfg, k, int(c[k]))
+        ccfg.self_attn = int(c["self_attn"])
+        ccfg.n_levels = len(c["c_hidden"])
+        for i in range(ccfg.n_levels):
+            ccfg.c_hidden[i], ccfg.nhead[i], ccfg.blocks[i] = c["c_hidden"][i], c["nhead"][i], c["blocks"][i]
+            ccfg.level_config[i].value = c["level_config"][i].encode()
+        h = ctypes.c_void_p()
+        check(L.pb200_paella_create(ctypes.byref(ccfg), ctypes.byref(h)), "pb200_paella_create")
+        m._handle = h
+        if L.pb200_paella_weight_bytes(h) != blob.numel():
+            raise PaellaB200Error(f"{path}: packed blob has {blob.numel()} bytes, this build's plan needs {L.pb200_paella_weight_bytes(h)} "
+                                  "(packed with a different library version or config)")
+        m._blob = blob
+        with torch.cuda.device(blob.device):
+            check(L.pb200_paella_bind_weights(h, ptr(blob)), "pb200_paella_bind_weights")
+        return m
 
     def _ws(self, nbytes: int) -> torch.Tensor:
         if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != self._device():
@@ -587,10 +634,20 @@ class Paella(nn.Module):
         with torch.cuda.device(dev):
             out = torch.empty(batch, h, w, dtype=torch.int64, device=dev)
             ws = self._ws(L.pb200_paella_workspace_bytes(self._handle, batch, h, w, 1))
-            seed, off = ops.take_philox(batch * h * w * self.num_labels, dev, generator)
-            check(L.pb200_paella_sample_tokens(self._handle, ptr(feats), batch, h * w, 1 if cfg is not None else 0,
-                                               float(cfg) if cfg is not None else 0.0, float(temperature), seed, off,
-                                               ptr(out), ptr(ws), ws.numel(), current_stream()), "pb200_paella_sample_tokens")
+            n = batch * h * w
+            chunks = ops.philox_row_chunks(n, self.num_labels)       # one kernel per 32-bit-indexable piece, like torch
+            flat = out.view(-1)
+            for lo, hi in chunks:
+                seed, off = ops.take_philox((hi - lo) * self.num_labels, dev, generator)
+                if len(chunks) == 1:
+                    f = feats
+                elif cfg is not None:
+                    f = torch.cat([feats[lo:hi], feats[n + lo:n + hi]])
+                else:
+                    f = feats[lo:hi]
+                check(L.pb200_paella_sample_tokens(self._handle, ptr(f), 1, hi - lo, 1 if cfg is not None else 0,
+                                                   float(cfg) if cfg is not None else 0.0, float(temperature), seed, off,
+                                                   ptr(flat[lo:hi]), ptr(ws), ws.numel(), current_stream()), "pb200_paella_sample_tokens")
         return out
 
     def forward(self, x, r, byt5, clip=None, clip_image=None, x_cat=None, **kwargs):
@@ -601,9 +658,28 @@ class Paella(nn.Module):
         if kwargs:
             raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
         B, H, W = x.shape
-        cond = self.prepare_conditioning([{"byt5": byt5, "clip": clip, "clip_image": clip_image}], (H, W))
+        cond = self._cond_for_forward(byt5, clip, clip_image, (H, W))
         feats = self.features(x, r, cond, attn_weights, B if attn_weights is not None else 0)
         return self.logits_from_features(feats, B, H, W)
+
+    def _cond_for_forward(self, byt5, clip, clip_image, hw):
+        """The reference's own loop calls ``model(x, t, **inputs)`` twice per step with the SAME conditioning tensors
+        (ref/src/utils.py:42-45): the conditioning cache (44 kv_mapper + K/V GEMMs) is memoised on the identity and version
+        of those tensor objects (references are held, so an address cannot be recycled under the memo) and the weights."""
+        self._ensure_packed()
+        ci = list(clip_image) if isinstance(clip_image, (list, tuple)) else [clip_image]
+        ts = [byt5, clip] + ci
+        try:
+            vers = tuple(None if t is None else t._version for t in ts)
+        except RuntimeError:        # inference tensors carry no version counter: no memo
+            vers = None
+        memo = self._cond_single
+        if (vers is not None and memo is not None and memo["hw"] == tuple(hw) and memo["vers"] == vers and len(memo["ts"]) == len(ts)
+                and all(a is b for a, b in zip(memo["ts"], ts)) and memo["key"] == self._packed_key):
+            return memo["cond"]
+        cond = self.prepare_conditioning([{"byt5": byt5, "clip": clip, "clip_image": clip_image}], hw, share_uniform=False)
+        self._cond_single = None if vers is None else {"hw": tuple(hw), "vers": vers, "ts": ts, "cond": cond, "key": self._packed_key}
+        return cond
 
     def add_noise(self, x, t, mask=None, random_x=None):
         """ref/src/modules.py:277-283 on torch's random stream."""

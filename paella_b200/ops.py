@@ -30,6 +30,30 @@ def take_philox(numel: int, device, generator: Optional[torch.Generator] = None)
     return seed, off
 
 
+def philox_row_chunks(rows: int, k: int, elem_bytes: int = 4):
+    """Row ranges [(lo, hi), ...] over which torch runs ONE distribution kernel each for a contiguous [rows, k] tensor.
+    TensorIterator splits an iteration space that is not 32-bit indexable (numel > INT32_MAX or last BYTE offset >
+    INT32_MAX, i.e. > 2^29 fp32 elements) into halves, first half first, recursively (ATen TensorIterator::split /
+    SplitUntil32Bit, DistributionTemplates.h:132-138); every sub-kernel takes its own Philox offset from the generator.
+    bs=64 at 32x32x8192 is exactly 2^29 elements (one kernel); larger batches split -- mirrored here so the draws stay
+    bit-identical to torch.multinomial's."""
+    lim = 2 ** 31 - 1
+
+    def split(n):
+        if n <= lim and 1 + (n - 1) * elem_bytes <= lim:
+            return [n]
+        half = n // 2
+        return split(half) + split(n - half)
+    out, lo = [], 0
+    for n in split(rows * k):
+        if n % k != 0:
+            raise _lib.PaellaB200Error(f"a {rows}x{k} draw splits inside a row under torch's 32-bit indexing rule; use a batch whose "
+                                       "row count is a power-of-two multiple")
+        out.append((lo, lo + n // k))
+        lo += n // k
+    return out
+
+
 # ------------------------------------------------------------------ random ops
 def randint(num_labels: int, size, device, generator=None) -> torch.Tensor:
     """torch.randint(0, num_labels, size, device=device)  [ref/src/utils.py:37]"""
@@ -51,9 +75,10 @@ def multinomial(p: torch.Tensor, generator=None) -> torch.Tensor:
     assert p.dim() == 2 and p.dtype == torch.float32
     p = p.contiguous()
     out = torch.empty(p.shape[0], dtype=torch.int64, device=p.device)
-    seed, off = take_philox(p.numel(), p.device, generator)
-    check(lib().pb200_multinomial(ptr(p), p.shape[0], p.shape[1], seed, off, ptr(out), current_stream()),
-          "pb200_multinomial")
+    for lo, hi in philox_row_chunks(p.shape[0], p.shape[1]):
+        seed, off = take_philox((hi - lo) * p.shape[1], p.device, generator)
+        check(lib().pb200_multinomial(ptr(p[lo:hi]), hi - lo, p.shape[1], seed, off, ptr(out[lo:hi]), current_stream()),
+              "pb200_multinomial")
     return out
 
 
@@ -66,11 +91,14 @@ def resample_logits(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], cf
     lu = logits_u.contiguous().float() if logits_u is not None else None
     out = torch.empty((B,) + tuple(logits_c.shape[2:]), dtype=torch.int64, device=lc.device)
     m = {"multinomial": 0, "argmax": 1}[mode]
-    seed, off = (0, 0)
-    if m == 0:
-        seed, off = take_philox(B * hw * K, lc.device, generator)
-    check(lib().pb200_resample_logits(ptr(lc), ptr(lu), B, K, hw, float(cfg), float(temperature), m, seed, off, ptr(out),
-                                      current_stream()), "pb200_resample_logits")
+    chunks = philox_row_chunks(B * hw, K) if m == 0 else [(0, B * hw)]
+    for lo, hi in chunks:
+        if lo % hw or hi % hw:
+            raise _lib.PaellaB200Error("resample_logits: torch's 32-bit split of this draw falls inside a sample")
+        b0, b1 = lo // hw, hi // hw
+        seed, off = take_philox((hi - lo) * K, lc.device, generator) if m == 0 else (0, 0)
+        check(lib().pb200_resample_logits(ptr(lc[b0:b1]), ptr(lu[b0:b1]) if lu is not None else None, b1 - b0, K, hw, float(cfg),
+                                          float(temperature), m, seed, off, ptr(out[b0:b1]), current_stream()), "pb200_resample_logits")
     return out
 
 
@@ -127,7 +155,7 @@ def vq_gather(idx: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------ GEMM (unit-test surface)
 def gemm_f16(a: torch.Tensor, w: torch.Tensor, mode: int, out: torch.Tensor, bias=None, resid=None, alpha: float = 1.0,
              sqsum=None, rows_per_sample: int = 0, film=None, film_off: int = 0, remap=(0, 0), up=(0, 0, 0), out16=None,
-             ln_stat=None, ln_wsum=None) -> torch.Tensor:
+             ln_stat=None, ln_wsum=None, ln_shift=None, ln_mean_out=None) -> torch.Tensor:
     """out = epilogue(a[M,K] @ w[N,K]^T); a, w fp16 contiguous."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.shape[1] == w.shape[1]
     M, K = a.shape
@@ -142,6 +170,8 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, mode: int, out: torch.Tensor, bia
     ep.ln_stat = ptr(ln_stat).value if ln_stat is not None else None
     ep.ln_wsum = ptr(ln_wsum).value if ln_wsum is not None else None
     ep.ln_c = K if mode == _lib.EPI_F16_LN else 0
+    ep.ln_shift = ptr(ln_shift).value if ln_shift is not None else None
+    ep.ln_mean_out = ptr(ln_mean_out).value if ln_mean_out is not None else None
     ep.resid = ptr(resid).value if resid is not None else None
     ep.ldr = resid.shape[-1] if resid is not None else 0
     ep.alpha = alpha

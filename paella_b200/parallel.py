@@ -26,10 +26,36 @@ def rank_seed(base_seed: int, rank: int) -> int:
     return base_seed + rank
 
 
-def broadcast_blob(blob: torch.Tensor, src: int = 0) -> torch.Tensor:
-    """The one collective of a multi-GPU run: the packed (fp16/fp32) weight blob, rank ``src`` -> all."""
+def blob_checksum(blob: torch.Tensor) -> torch.Tensor:
+    """64-bit wrap-around sum of the whole blob viewed as int64 words (+ the tail bytes): one pass over HBM."""
+    flat = blob.reshape(-1).view(torch.uint8)
+    n8 = flat.numel() // 8 * 8
+    s = flat[:n8].view(torch.int64).sum()
+    if n8 < flat.numel():
+        s = s + flat[n8:].to(torch.int64).sum()
+    return s.reshape(1)
+
+
+def assert_same_across_ranks(value: torch.Tensor, what: str = "value") -> None:
+    """Every rank holds the same int64 ``value`` (one tiny all-reduce: max(v) == -max(-v)), else raise on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    v = value.reshape(-1).to(torch.int64)
+    both = torch.cat([v, -v])
+    dist.all_reduce(both, op=dist.ReduceOp.MAX)
+    n = v.numel()
+    if not torch.equal(both[:n], -both[n:]):
+        raise RuntimeError(f"rank {dist.get_rank()}: {what} differs between ranks (max {both[:n].tolist()}, min {(-both[n:]).tolist()}, "
+                           f"mine {v.tolist()})")
+
+
+def broadcast_blob(blob: torch.Tensor, src: int = 0, verify: bool = True) -> torch.Tensor:
+    """The one collective of a multi-GPU run: the packed (fp16/fp32) weight blob, rank ``src`` -> all, followed by a
+    checksum agreement check (non-source ranks start from zeros: a short or skipped broadcast must not go unnoticed)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.broadcast(blob, src=src)
+        if verify:
+            assert_same_across_ranks(blob_checksum(blob), "packed weight blob checksum after broadcast")
     return blob
 
 

@@ -96,16 +96,32 @@ def load_conditional_models(byt5_model_name, vqgan_path, device):
     return vqgan, (byt5_tokenizer, byt5)
 
 
+def _decode_tail(tokens, decode, decode_output):
+    """The step after the path (ref/src_distributed/train.py:168-171, notebook nb:354-357): the final token
+    grid goes straight into the f4 decoder on the same stream -- no host round trip, no separate clamp / byte pass."""
+    if decode is None:
+        return tokens
+    if decode_output == "uint8":
+        return decode.decode_indices_u8(tokens)
+    if decode_output == "clamp":
+        return decode.decode_indices_clamped(tokens)
+    if decode_output == "raw":
+        return decode.decode_indices(tokens)
+    raise ValueError(f"decode_output={decode_output!r}: expected 'uint8', 'clamp' or 'raw'")
+
+
 def sample(model, model_inputs, latent_shape, unconditional_inputs=None, steps=12, renoise_steps=11, temperature=(1.0, 0.2),
-           cfg=8.0, t_start=1.0, t_end=0.0, device="cuda", exact=False):
+           cfg=8.0, t_start=1.0, t_end=0.0, device="cuda", exact=False, decode=None, decode_output="uint8"):
     """ref/src/utils.py:35-55 (same positional/keyword arguments; ``device`` is accepted and must be the model's).
-    ``exact=True`` materialises the logits and uses the op-for-op torch arithmetic (parity path)."""
+    ``exact=True`` materialises the logits and uses the op-for-op torch arithmetic (parity path).
+    ``decode=vqmodel`` appends the reference callers' next step, ``vqmodel.decode_indices(tokens).clamp(0, 1)``, fused on the
+    tail: returns uint8 NHWC images (``decode_output='uint8'``), clamped fp32 NCHW ('clamp') or unclamped fp32 NCHW ('raw')."""
     cfgs = [cfg] * steps if cfg else None
     if cfgs is not None and unconditional_inputs is None:
         raise TypeError("sample(): cfg is set but unconditional_inputs is None")
     out, _ = _sample_core(model, model_inputs, tuple(latent_shape), unconditional_inputs, None, steps, renoise_steps,
                           temperature, cfgs, t_start, t_end, steps, "multinomial", None, exact, False)
-    return out
+    return _decode_tail(out, decode, decode_output)
 
 
 def sample_distributed(model, model_inputs, unconditional_inputs, latent_shape, init_x=None, steps=12, renoise_steps=None,

@@ -65,7 +65,22 @@ class ResBlock(nn.Module):
                     nn.init.constant_(mod.bias, 0)
 
     def forward(self, x):
-        raise PaellaB200Error("vqgan.ResBlock.forward outside a VQModel is not wired to the CUDA library")
+        """ref/src/vqgan.py:36-42 on its own: NCHW fp32 in/out, the same kernels VQModel's plan runs (pb200_vqgan_resblock)."""
+        from .modules import _cached, _f32, _to_nchw, _to_rows, _w16
+        if x.dim() != 4 or x.shape[1] != self.norm1.normalized_shape[0]:
+            raise PaellaB200Error(f"vqgan.ResBlock({self.norm1.normalized_shape[0]}) got shape {tuple(x.shape)}")
+        B, c, H, W = x.shape
+        rows = _to_rows(x)
+        dw, l1, l2 = self.depthwise[1], self.channelwise[0], self.channelwise[2]
+        w9 = _cached(dw, "w9", dw.weight, lambda t: t.float().reshape(c, 9).t().contiguous())
+        gam = (ctypes.c_float * 6)(*[float(v) for v in self.gammas.detach().float().cpu()])
+        L = lib()
+        ws = torch.empty(L.pb200_vqgan_resblock_workspace_bytes(B, H, W, c), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(L.pb200_vqgan_resblock(ptr(rows), B, H, W, c, ptr(w9), ptr(_f32(dw.bias)), ptr(_w16(l1, "w16", l1.weight)),
+                                         ptr(_f32(l1.bias)), ptr(_w16(l2, "w16", l2.weight)), ptr(_f32(l2.bias)), gam, ptr(ws),
+                                         ws.numel(), current_stream()), "pb200_vqgan_resblock")
+        return _to_nchw(rows, x.shape)
 
 
 class VQModel(nn.Module):
@@ -110,7 +125,8 @@ class VQModel(nn.Module):
             pass
 
     def _device(self):
-        return self.vquantizer.codebook.weight.device
+        po = getattr(self, "_packed_only", None)
+        return po if po is not None else self.vquantizer.codebook.weight.device
 
     def _weights_key(self):
         return (str(self._device()),) + tuple((t.data_ptr(), t._version) for t in self.state_dict().values())
@@ -152,17 +168,55 @@ class VQModel(nn.Module):
                           f"pb200_vqgan_load_param({name.decode()})")
                 torch.cuda.current_stream().synchronize()
             if distributed:
-                dist.broadcast(self._blob, src=broadcast_src)
+                from .parallel import broadcast_blob
+                broadcast_blob(self._blob, src=broadcast_src)      # + checksum agreement across ranks (raises on mismatch)
+            # the library mirrors the six ResBlock gammas on the host (kernel arguments): refresh them from the blob now that
+            # it is complete on every rank (a rank that only received the broadcast never ran load_param)
+            check(L.pb200_vqgan_sync_params(self._handle, current_stream()), "pb200_vqgan_sync_params")
         self._packed_key = self._weights_key()
         return self
 
     def _ensure_packed(self):
+        if getattr(self, "_packed_only", None) is not None:
+            return
         if self._handle is None or self._packed_key != self._weights_key():
             self.pack_weights()
 
     def _apply(self, fn, *a, **k):
+        if getattr(self, "_packed_only", None) is not None:
+            return self
         self._packed_key = None
         return super()._apply(fn, *a, **k)
+
+    # -------------------------------------------------------------- on-disk packed form
+    def save_packed(self, path: str):
+        """Packed blob + config of this codec -> ``path`` (tools/pack_checkpoint.py does this for ``vqgan_f4.pt``, nb:157)."""
+        from .packed import save_blob
+        self._ensure_packed()
+        save_blob(path, "vqgan", dict(self._cfg), self._blob)
+
+    @classmethod
+    def from_packed(cls, path: str, device="cuda"):
+        from .packed import load_blob
+        cfg, blob = load_blob(path, "vqgan", device)
+        with torch.device("meta"):
+            m = cls(**cfg)
+        m.eval().requires_grad_(False)
+        L = lib()
+        m._packed_only = blob.device
+        ccfg = _lib.VqganConfig()
+        for k in ("levels", "bottleneck_blocks", "c_hidden", "c_latent", "codebook_size"):
+            setattr(ccfg, k, int(cfg[k]))
+        ccfg.scale_factor = float(cfg["scale_factor"])
+        h = ctypes.c_void_p()
+        check(L.pb200_vqgan_create(ctypes.byref(ccfg), ctypes.byref(h)), "pb200_vqgan_create")
+        m._handle = h
+        if L.pb200_vqgan_weight_bytes(h) != blob.numel():
+            raise PaellaB200Error(f"{path}: packed blob has {blob.numel()} bytes, this build's plan needs {L.pb200_vqgan_weight_bytes(h)}")
+        m._blob = blob
+        with torch.cuda.device(blob.device):
+            check(L.pb200_vqgan_bind_weights(h, ptr(blob)), "pb200_vqgan_bind_weights")      # gammas are re-read lazily
+        return m
 
     def _ws(self, nbytes):
         if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != self._device():
@@ -189,7 +243,7 @@ class VQModel(nn.Module):
         mse = torch.mean((qe - lat) ** 2)
         return qe / self.scale_factor, lat / self.scale_factor, idx, mse + mse * 0.25
 
-    def _decode(self, idx, lat):
+    def _decode(self, idx, lat, mode=_lib.IMG_F32_NCHW):
         self._ensure_packed()
         L, dev = lib(), self._device()
         with torch.cuda.device(dev):
@@ -199,10 +253,13 @@ class VQModel(nn.Module):
             else:
                 lat = lat.to(device=dev, dtype=torch.float32).contiguous()
                 B, _, h, w = lat.shape
-            img = torch.empty(B, 3, 4 * h, 4 * w, dtype=torch.float32, device=dev)
+            if mode == _lib.IMG_U8_NHWC:
+                img = torch.empty(B, 4 * h, 4 * w, 3, dtype=torch.uint8, device=dev)
+            else:
+                img = torch.empty(B, 3, 4 * h, 4 * w, dtype=torch.float32, device=dev)
             ws = self._ws(L.pb200_vqgan_workspace_bytes(self._handle, B, 4 * h, 4 * w))
-            check(L.pb200_vqgan_decode(self._handle, ptr(idx), ptr(lat), B, h, w, ptr(img), ptr(ws), ws.numel(),
-                                       current_stream()), "pb200_vqgan_decode")
+            check(L.pb200_vqgan_decode_ex(self._handle, ptr(idx), ptr(lat), B, h, w, ptr(img), mode, ptr(ws), ws.numel(),
+                                          current_stream()), "pb200_vqgan_decode_ex")
         return img
 
     def decode(self, x):
@@ -212,6 +269,15 @@ class VQModel(nn.Module):
     def decode_indices(self, x):
         """ref/src/vqgan.py:103-107 (no scale_factor on this path, as in the reference)."""
         return self._decode(x, None)
+
+    def decode_indices_clamped(self, x):
+        """``decode_indices(x).clamp(0, 1)`` (ref/src_distributed/train.py:168-171) with the clamp fused into the decoder's last kernel."""
+        return self._decode(x, None, _lib.IMG_F32_NCHW_CLAMP01)
+
+    def decode_indices_u8(self, x):
+        """uint8 NHWC images [B,4h,4w,3]: ``decode_indices(x).clamp(0,1)`` followed by torchvision save_image's byte conversion
+        (``mul(255).add_(0.5).clamp_(0,255).to(uint8)`` on the HWC view), fused into the decoder's last kernel."""
+        return self._decode(x, None, _lib.IMG_U8_NHWC)
 
     def forward(self, x, quantize=False):
         qe, x, _, vq_loss = self.encode(x, quantize)

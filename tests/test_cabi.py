@@ -31,7 +31,7 @@ def test_ctypes_table_mirrors_header():
     from paella_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _header_functions()
     l = _lib.lib()
-    assert l.pb200_abi_version() == 1
+    assert l.pb200_abi_version() == 2
     assert l.pb200_last_error() is not None
 
 

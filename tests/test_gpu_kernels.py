@@ -207,11 +207,11 @@ def test_gemm_plain_f32_f16(M, N, K):
     torch.cuda.synchronize()
     err = float((out - want).abs().max())
     _log("gemm_f32", {"M": M, "N": N, "K": K, "max_abs_err": err, "nan": int(torch.isnan(out).sum())})
-    assert err < 2e-3, err
+    assert err < 2e-4, err          # measured <= 4.2e-5 (profiles/r01_kernel_parity_final.jsonl)
     out16 = torch.zeros(M, N, device=DEV, dtype=torch.float16)
     ops.gemm_f16(a, w, _lib.EPI_F16, out16, bias=None)
     err16 = float((out16.float() - _ref_mm(a, w)).abs().max())
-    assert err16 < 2e-2, err16
+    assert err16 < 4e-3, err16      # half an fp16 ulp of |v| < 8 is 1.95e-3
 
 
 @pytest.mark.parametrize("M,N,K,P", [(512, 256, 128, 64), (8192, 5120, 1280, 64), (2048, 2560, 640, 16), (300, 128, 64, 100),
@@ -232,7 +232,7 @@ def test_gemm_gelu_sqsum(M, N, K, P):
     want_sq = (h * h).view(M // P, P, N).sum(1)
     rel = float(((sq.double() / 2 ** 24 - want_sq).abs() / (want_sq.abs() + 1e-3)).max())
     _log("gemm_gelu", {"M": M, "N": N, "K": K, "P": P, "max_abs_err": err, "sq_rel": rel})
-    assert err < 1e-2 and rel < 2e-3
+    assert err < 4e-3 and rel < 1e-4          # measured 1.96e-3 (fp16 half-ulp of the stored value) / 2.2e-5
 
 
 @pytest.mark.parametrize("M,N,K,P", [(1024, 1280, 5120, 64), (8192, 1280, 1280, 64), (12032, 512, 256, 64)])
@@ -255,7 +255,7 @@ def test_gemm_resid_film_inplace(M, N, K, P):
     ops.gemm_f16(a, w, _lib.EPI_RESID_F32, xin, bias=bias, resid=xin, alpha=0.5, rows_per_sample=P, film=film8, film_off=8)
     err = float((xin - want).abs().max())
     _log("gemm_resid", {"M": M, "N": N, "K": K, "max_abs_err": err})
-    assert err < 3e-3
+    assert err < 1e-4          # measured <= 2.1e-5
 
 
 @pytest.mark.parametrize("M,C,N,P", [(8192, 1280, 3840, 64), (1024, 128, 384, 16), (300, 64, 96, 100)])
@@ -295,7 +295,44 @@ def test_gemm_layernorm_folded_across_two_gemms(M, C, N, P):
     err = float((out.float() - want).abs().max())
     rms = float((out.float() - want).pow(2).mean().sqrt())
     _log("gemm_ln_fold", {"M": M, "C": C, "N": N, "max_abs_err": err, "rms": rms})
-    assert err < 3e-2 and rms < 4e-3, (err, rms)
+    assert err < 6e-3 and rms < 9e-4, (err, rms)          # measured 2.4e-3 / 3.0e-4
+
+
+@pytest.mark.parametrize("M,C,N,offset", [(8192, 1280, 3840, 40.0), (1024, 128, 384, 300.0)])
+def test_gemm_layernorm_fold_with_row_shift_is_offset_invariant(M, C, N, offset):
+    """Rows with |mean| / std = 20..150 (a residual stream carrying a large offset): with the per-row shift (here the true
+    row mean perturbed by half a std, as if taken from the previous AttnBlock) the folded LayerNorm stays within the SAME
+    bound as the zero-mean case; without it the fp16 copy would lose log2(ratio) bits.  Also checks the consumer's
+    ln_mean_out = shift + mean' (the next block's shift)."""
+    from paella_b200 import _lib
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(12)
+    K1 = 256
+    a = torch.randn(M, K1, device=DEV, generator=g).half()
+    w1 = (torch.randn(C, K1, device=DEV, generator=g) / math.sqrt(K1)).half()
+    b1 = torch.randn(C, device=DEV, generator=g)
+    x0 = torch.randn(M, C, device=DEV, generator=g) * 2 + offset * (1 + 0.1 * torch.randn(M, 1, device=DEV, generator=g))
+    y = _ref_mm(a, w1) + b1 + x0
+    shift = (y.mean(1) + torch.randn(M, device=DEV, generator=g)).contiguous()
+    x = x0.clone()
+    x16 = torch.full((M, C), float("nan"), device=DEV, dtype=torch.float16)
+    stat = torch.zeros(M, 2, device=DEV, dtype=torch.int64)
+    ops.gemm_f16(a, w1, _lib.EPI_RESID_LN_F32, x, bias=b1, resid=x, out16=x16, ln_stat=stat, ln_shift=shift)
+    assert float((x - y).abs().max()) < 1e-3 * max(1.0, offset / 40)          # the fp32 stream itself is NOT shifted
+    assert torch.equal(x16, (x - shift[:, None]).half())
+    w2 = (torch.randn(N, C, device=DEV, generator=g) / math.sqrt(C)).half()
+    b2 = torch.randn(N, device=DEV, generator=g) * 0.1
+    wsum = w2.float().sum(1).contiguous()
+    want = (torch.nn.functional.layer_norm(x.double(), (C,), eps=1e-6) @ w2.double().t() + b2.double()).float()
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
+    mean_out = torch.full((M,), float("nan"), device=DEV)
+    ops.gemm_f16(x16, w2, _lib.EPI_F16_LN, out, bias=b2, ln_stat=stat, ln_wsum=wsum, ln_shift=shift, ln_mean_out=mean_out)
+    err = float((out.float() - want).abs().max())
+    rms = float((out.float() - want).pow(2).mean().sqrt())
+    mean_err = float((mean_out.double() - x.double().mean(1)).abs().max())
+    _log("gemm_ln_fold_shift", {"M": M, "C": C, "N": N, "offset": offset, "max_abs_err": err, "rms": rms, "mean_err": mean_err})
+    assert err < 6e-3 and rms < 9e-4, (err, rms)
+    assert mean_err < 1e-3 * max(1.0, offset / 40)
 
 
 def test_gemm_unpatchify_and_nchw_and_remap():

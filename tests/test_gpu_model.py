@@ -5,7 +5,8 @@
 Tolerances: the CUDA path rounds GEMM operands to fp16 (fp32 accumulate, fp32 residual stream).  Emulating
 exactly that rounding in the oracle (oracle.paella_oracle.mm_f16_operands) moves the default model's logits
 (std 0.18) by 8e-4 max / 1.4e-4 rms; the kernels add fp16 storage of the MLP hidden, q/k/v and softmax
-weights.  Bounds below: 1e-2 max-abs, 2e-3 rms on logits.
+weights.  Bounds below are <= 3x what was measured on B200 (profiles/r01_model_parity_final.jsonl): default 1.008 B model
+7.4e-4 / 1.3e-4 (max-abs / rms; logit std 0.177) -> 2.5e-3 / 4e-4; tiny golden model 2.7e-3 / 4.2e-4 -> 7e-3 / 1.2e-3.
 """
 import json
 import os
@@ -17,7 +18,8 @@ from helpers import load_golden, oracle_cfg, t
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-MAX_ABS, RMS = 1e-2, 2e-3
+MAX_ABS, RMS = 7e-3, 1.2e-3             # tiny golden config
+MAX_ABS_D, RMS_D = 2.5e-3, 4e-4         # reference-default config
 
 
 def _log(name, payload):
@@ -79,7 +81,7 @@ def test_tiny_r_and_c_embeddings_match_reference_golden(tiny):
     assert ce.shape == tuple(g["c_embed"].shape)
     mx, rms = _errs(ce, t(g["c_embed"]))
     _log("tiny_c_embed", {"max_abs": mx, "rms": rms})
-    assert mx < 5e-3
+    assert mx < 3.5e-3 and rms < 9e-4          # measured 1.26e-3 / 3.0e-4
     ce2 = m.gen_c_embeddings(t(g["byt5"]).to(DEV), None, [t(g["clip_image"]).to(DEV)] * 2)
     assert ce2.shape == (2, 5 + 8, cfg["c_cond"])
 
@@ -212,7 +214,7 @@ def test_default_config_forward_vs_oracle(default_model):
     mx, rms = _errs(got, want)
     top1 = float((got.cpu().argmax(1) == want.argmax(1)).float().mean())
     _log("default_forward", {"max_abs": mx, "rms": rms, "logit_std": float(want.std()), "top1_agree": top1})
-    assert mx < MAX_ABS and rms < RMS
+    assert mx < MAX_ABS_D and rms < RMS_D
     assert top1 > 0.97
 
 
@@ -230,7 +232,7 @@ def test_default_config_forward_64x64_vs_oracle(default_model):
     mx, rms = _errs(got, want)
     top1 = float((got.cpu().argmax(1) == want.argmax(1)).float().mean())
     _log("default_forward_64x64", {"max_abs": mx, "rms": rms, "logit_std": float(want.std()), "top1_agree": top1})
-    assert mx < MAX_ABS and rms < RMS
+    assert mx < MAX_ABS_D and rms < RMS_D
     assert top1 > 0.97
 
 

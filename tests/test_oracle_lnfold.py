@@ -8,7 +8,11 @@ import pytest
 import torch
 
 
-def _folded(x, w16, bias, c):
+def _folded(x, w16, bias, c, shift=None):
+    """shift: per-row fp32 scalar subtracted by the producer before the fp16 copy and the statistics (LayerNorm is
+    invariant under it); the executor passes the row mean the previous AttnBlock of the same stream saw."""
+    if shift is not None:
+        x = x - shift[:, None]
     x16 = x.half()
     s = torch.round(x.double().sum(1) * 2 ** 20) / 2 ** 20            # per-row sum, 2^-20 fixed point
     q = torch.round((x.double() ** 2).sum(1) * 2 ** 16) / 2 ** 16     # per-row sum of squares, 2^-16 fixed point
@@ -38,6 +42,22 @@ def test_fold_error_grows_with_mean_over_std(ratio, bound):
     # outputs are O(1): the plain path's error is the fp16 rounding of LN(x) and of the result (~2e-3)
     assert e_plain < 4e-3
     assert e_fold < bound, (ratio, e_fold, e_plain)
+
+
+@pytest.mark.parametrize("ratio", [4.0, 16.0, 64.0])
+def test_shifted_fold_is_as_accurate_as_the_plain_path(ratio):
+    """With the per-row shift (the previous block's row mean: here the true mean perturbed by 30 % of a std, far more than
+    one block changes it) the fold's error no longer depends on |mean| / std."""
+    g = torch.Generator().manual_seed(1)
+    M, C, N = 512, 1280, 384
+    x = torch.randn(M, C, generator=g) * 1.7 + ratio * 1.7
+    w16 = (torch.randn(N, C, generator=g) / C ** 0.5).half()
+    bias = torch.randn(N, generator=g) * 0.1
+    shift = x.mean(1) + 0.3 * 1.7 * torch.randn(M, generator=g)
+    exact = torch.nn.functional.layer_norm(x.double(), (C,), eps=1e-6) @ w16.double().t() + bias.double()
+    e_fold = float((_folded(x, w16, bias, C, shift).double() - exact).abs().max())
+    e_plain = float((_plain(x, w16, bias, C).double() - exact).abs().max())
+    assert e_plain < 4e-3 and e_fold < 4e-3, (ratio, e_fold, e_plain)
 
 
 def test_fixed_point_statistics_cover_the_residual_stream_range():

@@ -31,7 +31,17 @@ def _worker(rank, world, port, total, ret):
     sizes = [P.shard_range(total, r, world)[1] - P.shard_range(total, r, world)[0] for r in range(world)]
     full = P.gather_tokens(toks, sizes)
     ok_gather = bool((full[:, 0, 0] == torch.arange(total)).all())
-    ret[rank] = (lo, hi, ok_blob, ok_gather, P.rank_seed(1234, rank))
+    # a receiver whose blob differs from the source's (short / skipped broadcast) must be caught on EVERY rank
+    bad = blob.clone()
+    if rank == 1:
+        bad[1000] ^= 1
+    caught = False
+    try:
+        P.assert_same_across_ranks(P.blob_checksum(bad), "blob checksum")
+    except RuntimeError:
+        caught = True
+    P.assert_same_across_ranks(P.blob_checksum(blob), "blob checksum")      # and the good one passes
+    ret[rank] = (lo, hi, ok_blob, ok_gather, P.rank_seed(1234, rank), caught)
     dist.destroy_process_group()
 
 
@@ -43,6 +53,18 @@ def test_two_rank_shard_broadcast_gather():
     assert ret[0][:2] == (0, 4) and ret[1][:2] == (4, 7)
     assert all(ret[r][2] and ret[r][3] for r in range(world))
     assert ret[0][4] != ret[1][4]
+    assert ret[0][5] and ret[1][5]          # the corrupted receiver was detected by both ranks
+
+
+def test_blob_checksum_sees_every_byte():
+    from paella_b200.parallel import blob_checksum
+    g = torch.Generator().manual_seed(0)
+    b = torch.randint(0, 256, (4099,), dtype=torch.uint8, generator=g)       # not a multiple of 8: the tail bytes count too
+    ref = int(blob_checksum(b))
+    for pos in (0, 7, 8, 2049, 4095, 4098):
+        c = b.clone()
+        c[pos] = (int(c[pos]) + 1) % 256
+        assert int(blob_checksum(c)) != ref, pos
 
 
 def test_shard_range_partitions():
