@@ -474,7 +474,7 @@ def main():
     prof = json.loads(cbuf.value.decode())
     L.pb200_profile_enable(0)
     pk = peaks()
-    tensor_tags = [k for k in prof if k.startswith("gemm") or k.startswith("conv") or k in ("attention_tc",)]
+    tensor_tags = [k for k in prof if k.startswith("gemm") or k.startswith("conv")]
     gemm_ms = sum(prof[k]["ms"] for k in tensor_tags)
     gemm_fl = sum(prof[k]["work"] for k in tensor_tags)
     gemm_n = sum(prof[k]["launches"] for k in tensor_tags)

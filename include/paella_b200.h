@@ -164,10 +164,11 @@ int pb200_cast_f16(const float* x, int64_t n, int silu, void* out16, void* strea
 int pb200_dwconv_ln(const float* x, const float* skip, const float* w_packed, const float* bias, int batch, int h, int w,
                     int c, int k, void* out16, void* stream);
 /* GlobalResponseNorm in place on the fp16 hidden [batch, rows_per_sample, n] of a PB200_EPI_GELU_F16 GEMM whose
- * epilogue accumulated sqsum (2^-24 fixed point); zeroes zero_per_sample entries per sample of sqsum_next
+ * epilogue accumulated sqsum (2^-24 fixed point); zeroes zero_per_sample entries per sample of sqsum_next;
+ * scale_scratch = caller-owned fp32 [batch, n] (the per-sample multipliers 1 + gamma * Nx, written then read)
  * [ref/src/modules.py:30-40] */
 int pb200_grn_f16(void* h16, int batch, int rows_per_sample, int n, const uint64_t* sqsum, uint64_t* sqsum_next,
-                  int zero_per_sample, const float* gamma, const float* beta, void* stream);
+                  int zero_per_sample, const float* gamma, const float* beta, float* scale_scratch, void* stream);
 /* GlobalResponseNorm.forward on an fp32 NHWC tensor [batch, rows_per_sample, n]; stat = scratch [batch, n]
  * [ref/src/modules.py:37-40] */
 int pb200_grn_f32(const float* x, int batch, int rows_per_sample, int n, const float* gamma, const float* beta, float* stat,

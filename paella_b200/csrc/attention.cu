@@ -245,6 +245,10 @@ int launch_attention(const AttnParams& p, cudaStream_t st) {
     const int hd = p.E / p.nhead;
     PB_CHECK(p.E % 8 == 0, "attention: E must be a multiple of 8");
     if (p.B == 0 || p.P == 0) return 0;
+    {
+        const int rc = launch_attention_tc(p, st);
+        if (rc >= 0) return rc;
+    }
     // algorithmic bytes: q, self k/v, out once; conditioning k/v once per sample
     ProfScope prof("attention", 2.0 * ((double)p.B * p.P * 4.0 * p.E + (double)p.B * p.S_max * 2.0 * p.E), st);
     dim3 grid(ceil_div(p.P, ATT_BM), p.nhead, p.B);

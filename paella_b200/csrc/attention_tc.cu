@@ -1,0 +1,446 @@
+// Blackwell-native attention core for head_dim 80 (the reference model's 1280 / 16): tcgen05.mma with the S and O
+// accumulators in TMEM, Q/K/V staged by TMA, softmax straight out of TMEM.
+//   softmax(q k^T / sqrt(hd)) v over keys = [self tokens ; conditioning tokens]      ref/src/modules.py:12-19
+//   post-softmax, un-renormalised attn_weights on the last keys                     ref/utils/alter_attention.py:19-36
+//
+// One persistent CTA per SM walks (sample, head) units; a unit's K/V tile ([self ; cond] keys x 80) is loaded ONCE and
+// serves all of its 64-query tiles (1 at 32x32 latents, 4 on the 64x64-latent level).  Per query tile:
+//   MMA1   S[64 x keys] = Q K^T          M=64, N=keys (<= 256 per instruction), K = 80 = 4 x 16 (128B-swizzle atom) + 16 (32B atom)
+//   softmax  rows straight from TMEM (tcgen05.ld 32x32b): all keys of a row are resident, so ONE pass of max + exp2 -- no online
+//            rescaling; P (fp16) is written to shared memory in the K-major 128B-swizzle layout the next MMA reads
+//   MMA2   O[64 x 80] = P V              V is consumed as it lies in memory (keys x head_dim = "MN-major" B operand), N = 64 + 16
+//   epilogue O / rowsum -> fp16 -> global
+// Head dim 80 is not a multiple of the 64-element swizzle atom: every operand is split into a [rows x 64] tile (128-byte rows,
+// SWIZZLE_128B) and a [rows x 16] tile (32-byte rows, SWIZZLE_32B), loaded by two TMA boxes and multiplied by separate
+// tcgen05.mma instructions (same accumulator along K for Q/K, adjacent accumulator columns along N for V).
+// An M=64 accumulator occupies 16 lanes of each of the four TMEM sub-partitions (row r -> lane 32*(r/16) + r%16; CUTLASS
+// cute/atom/mma_traits_sm100.hpp tmem_frg, M_MMA == 64), so each softmax / epilogue warp owns 16 query rows.
+// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer + TMEM allocator, 4-7 softmax, 8-11 epilogue (2-3 idle: a warp may
+// only touch the TMEM lanes of sub-partition warp_id % 4).  Pipelines (mbarriers): Q ring (2), K/V ring (2, or 1 when the tile
+// is large), S accumulators (2 if 2*keys + 80 <= 512 TMEM columns), P buffers (2 if shared memory allows), one O accumulator.
+#include "attention.cuh"
+#include "gemm.cuh"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace pb {
+namespace {
+
+constexpr int TC_HD = 80;
+constexpr int TC_QT = 64;
+constexpr int TC_THREADS = 384;
+constexpr int TC_O_COLS = 80;
+
+struct TcParams {
+    int B, P, nhead, E, S_max;
+    int n_qt;          // query tiles per (sample, head)
+    int self_rows;     // self keys in the K/V tile (P, or 0 without self-attention)
+    int sbox;          // rows of one conditioning TMA box
+    int n1;            // S columns = MMA1 N = self_rows + sbox (multiple of 16)
+    int nkv, nsb, npb; // ring depths: K/V stages, S accumulators, P buffers
+    const int* kv_len;
+    const int* kv_slot;
+    float scale_log2;
+    const float* attn_w;
+    int n_w, w_batch;
+    __half* out;
+    uint32_t off_q;                 // 2 x [Q64 (8192 B) | Q16 (2048 B)]
+    uint32_t off_kv, kv_bytes;      // nkv x [K64 | V64 | K16 | V16]
+    uint32_t k64_bytes, k16_bytes;
+    uint32_t off_p, p_bytes;        // npb x ceil(n1 / 64) atoms of 8192 B
+    uint32_t off_invl;              // 4 x 64 floats
+    uint32_t off_bar;
+};
+
+constexpr uint32_t Q_BYTES = TC_QT * 160;      // one query tile: 64 x (128 + 32) bytes
+
+// barrier slots (8 bytes each)
+enum { BAR_QF = 0, BAR_QE = 2, BAR_KVF = 4, BAR_KVE = 6, BAR_SF = 8, BAR_SE = 10, BAR_PF = 12, BAR_PE = 14, BAR_OF = 16, BAR_OE = 17,
+       BAR_COUNT = 18 };
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
+                    const __grid_constant__ CUtensorMap tm_s64, const __grid_constant__ CUtensorMap tm_s16,
+                    const __grid_constant__ CUtensorMap tm_c64, const __grid_constant__ CUtensorMap tm_c16, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));       // generic pointer to the aligned base
+    const uint32_t bar0 = smem_base + p.off_bar;
+    auto bar = [&](int slot) { return bar0 + 8u * (uint32_t)slot; };
+    const uint32_t tmem_slot = bar0 + 8u * BAR_COUNT;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + p.off_bar + 8 * BAR_COUNT);
+    float* invl = reinterpret_cast<float*>(smem_gen + p.off_invl);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int units = p.B * p.nhead;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_q64); ptx::prefetch_tensormap(&tm_q16);
+        ptx::prefetch_tensormap(&tm_s64); ptx::prefetch_tensormap(&tm_s16);
+        ptx::prefetch_tensormap(&tm_c64); ptx::prefetch_tensormap(&tm_c16);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_init(bar(BAR_QF + i), 1);  ptx::mbar_init(bar(BAR_QE + i), 1);
+                ptx::mbar_init(bar(BAR_KVF + i), 1); ptx::mbar_init(bar(BAR_KVE + i), 1);
+                ptx::mbar_init(bar(BAR_SF + i), 1);  ptx::mbar_init(bar(BAR_SE + i), 4);
+                ptx::mbar_init(bar(BAR_PF + i), 4);  ptx::mbar_init(bar(BAR_PE + i), 1);
+            }
+            ptx::mbar_init(bar(BAR_OF), 1);
+            ptx::mbar_init(bar(BAR_OE), 4);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t col_o = (uint32_t)(p.nsb * p.n1);
+    pdl_launch_dependents();
+
+    auto q64 = [&](int qs) { return smem_base + p.off_q + (uint32_t)qs * Q_BYTES; };
+    auto q16 = [&](int qs) { return q64(qs) + TC_QT * 128; };
+    auto kv_stage = [&](int st) { return smem_base + p.off_kv + (uint32_t)st * p.kv_bytes; };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0, uc = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
+                const int b = u / p.nhead, h = u - b * p.nhead;
+                const int slot = p.kv_slot ? p.kv_slot[b] : b;
+                const int st = uc % p.nkv;
+                ptx::mbar_wait(bar(BAR_KVE + st), (((uint32_t)(uc / p.nkv)) & 1u) ^ 1u);
+                const uint32_t fb = bar(BAR_KVF + st);
+                ptx::mbar_arrive_expect_tx(fb, 2u * (uint32_t)(p.self_rows + p.sbox) * 160u);
+                const uint32_t k64 = kv_stage(st), v64 = k64 + p.k64_bytes, k16 = v64 + p.k64_bytes, v16 = k16 + p.k16_bytes;
+                const int hc = h * TC_HD;
+                if (p.self_rows) {
+                    const int row0 = b * p.P;
+                    ptx::tma_load_2d(&tm_s64, fb, k64, p.E + hc, row0);
+                    ptx::tma_load_2d(&tm_s64, fb, v64, 2 * p.E + hc, row0);
+                    ptx::tma_load_2d(&tm_s16, fb, k16, p.E + hc + 64, row0);
+                    ptx::tma_load_2d(&tm_s16, fb, v16, 2 * p.E + hc + 64, row0);
+                }
+                const int crow = slot * p.S_max;
+                ptx::tma_load_2d(&tm_c64, fb, k64 + (uint32_t)p.self_rows * 128u, hc, crow);
+                ptx::tma_load_2d(&tm_c64, fb, v64 + (uint32_t)p.self_rows * 128u, p.E + hc, crow);
+                ptx::tma_load_2d(&tm_c16, fb, k16 + (uint32_t)p.self_rows * 32u, hc + 64, crow);
+                ptx::tma_load_2d(&tm_c16, fb, v16 + (uint32_t)p.self_rows * 32u, p.E + hc + 64, crow);
+                for (int qt = 0; qt < p.n_qt; ++qt, ++it) {
+                    const int qs = it & 1;
+                    ptx::mbar_wait(bar(BAR_QE + qs), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(BAR_QF + qs), Q_BYTES);
+                    ptx::tma_load_2d(&tm_q64, bar(BAR_QF + qs), q64(qs), hc, b * p.P + qt * TC_QT);
+                    ptx::tma_load_2d(&tm_q16, bar(BAR_QF + qs), q16(qs), hc + 64, b * p.P + qt * TC_QT);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const int n1a = p.n1 > 256 ? 256 : p.n1, n1b = p.n1 - n1a;
+        const uint32_t idesc1a = ptx::umma_idesc_f16_major(TC_QT, n1a, 0, 0);
+        const uint32_t idesc1b = ptx::umma_idesc_f16_major(TC_QT, n1b > 0 ? n1b : 16, 0, 0);
+        constexpr uint32_t idesc2_64 = ptx::umma_idesc_f16_major(TC_QT, 64, 0, 1);
+        constexpr uint32_t idesc2_16 = ptx::umma_idesc_f16_major(TC_QT, 16, 0, 1);
+        // item cursor: (unit counter, unit, query tile, item index)
+        struct Cur { int uc, u, qt, it; };
+        auto valid = [&](const Cur& c) { return c.u < units; };
+        auto next = [&](Cur c) {
+            ++c.it;
+            if (++c.qt == p.n_qt) { c.qt = 0; c.u += gridDim.x; ++c.uc; }
+            return c;
+        };
+        // S = Q K^T of item c into its S accumulator
+        auto issue_s = [&](const Cur& c) {
+            const int st = c.uc % p.nkv;
+            if (c.qt == 0) ptx::mbar_wait(bar(BAR_KVF + st), ((uint32_t)(c.uc / p.nkv)) & 1u);
+            const int qs = c.it & 1, sb = c.it % p.nsb;
+            ptx::mbar_wait(bar(BAR_QF + qs), ((uint32_t)(c.it >> 1)) & 1u);
+            ptx::mbar_wait(bar(BAR_SE + sb), (((uint32_t)(c.it / p.nsb)) & 1u) ^ 1u);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+                const uint32_t k64 = kv_stage(st), k16 = k64 + 2 * p.k64_bytes;
+                const uint32_t d = tmem_base + (uint32_t)(sb * p.n1);
+#pragma unroll
+                for (int ks = 0; ks < 5; ++ks) {
+                    const uint64_t da = ks < 4 ? ptx::umma_desc_sw128(q64(qs)) + 2 * ks : ptx::umma_desc_sw32(q16(qs));
+                    const uint64_t db = ks < 4 ? ptx::umma_desc_sw128(k64) + 2 * ks : ptx::umma_desc_sw32(k16);
+                    ptx::umma_f16(d, da, db, idesc1a, ks != 0);
+                    if (n1b > 0) {      // keys 256.. : the K tile 256 rows further down
+                        const uint64_t db2 = ks < 4 ? ptx::umma_desc_sw128(k64 + 256u * 128u) + 2 * ks : ptx::umma_desc_sw32(k16 + 256u * 32u);
+                        ptx::umma_f16(d + 256u, da, db2, idesc1b, ks != 0);
+                    }
+                }
+                ptx::umma_commit(bar(BAR_SF + sb));
+                ptx::umma_commit(bar(BAR_QE + qs));
+            }
+            __syncwarp();
+        };
+        // O = P V of item c
+        auto issue_o = [&](const Cur& c) {
+            const int st = c.uc % p.nkv, pb = c.it % p.npb;
+            const int b = c.u / p.nhead;
+            const int slot = p.kv_slot ? p.kv_slot[b] : b;
+            const int nk = p.self_rows + (p.kv_len ? p.kv_len[slot] : p.S_max);
+            const int nks = (nk + 15) >> 4;
+            ptx::mbar_wait(bar(BAR_PF + pb), ((uint32_t)(c.it / p.npb)) & 1u);
+            ptx::mbar_wait(bar(BAR_OE), (((uint32_t)c.it) & 1u) ^ 1u);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+                const uint32_t v64 = kv_stage(st) + p.k64_bytes, v16 = v64 + p.k64_bytes + p.k16_bytes;
+                const uint32_t pt = smem_base + p.off_p + (uint32_t)pb * p.p_bytes;
+                const uint32_t d = tmem_base + col_o;
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint64_t da = ptx::umma_desc_sw128(pt + (uint32_t)(ks >> 2) * 8192u) + 2 * (ks & 3);
+                    ptx::umma_f16(d, da, ptx::umma_desc_sw128(v64 + (uint32_t)ks * 2048u), idesc2_64, ks != 0);
+                    ptx::umma_f16(d + 64u, da, ptx::umma_desc_sw32(v16 + (uint32_t)ks * 512u), idesc2_16, ks != 0);
+                }
+                ptx::umma_commit(bar(BAR_OF));
+                ptx::umma_commit(bar(BAR_PE + pb));
+                if (c.qt == p.n_qt - 1) ptx::umma_commit(bar(BAR_KVE + st));
+            }
+            __syncwarp();
+        };
+        Cur c{0, (int)blockIdx.x, 0, 0};
+        if (valid(c)) issue_s(c);
+        while (valid(c)) {
+            const Cur n = next(c);
+            // S of the next tile overlaps this tile's softmax when it has its own accumulator and (across units) its own K/V stage
+            const bool ahead = valid(n) && p.nsb == 2 && (n.uc == c.uc || p.nkv == 2);
+            if (ahead) issue_s(n);
+            issue_o(c);
+            if (valid(n) && !ahead) issue_s(n);
+            c = n;
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== softmax: S (TMEM) -> P (shared, fp16, K-major 128B swizzle) =====================
+        const int wq = warp & 3;
+        const int row = wq * 16 + lane;                 // query row of this thread inside the tile (lanes 16..31 carry none)
+        const bool lane_ok = lane < 16;
+        int it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int b = u / p.nhead;
+            const int slot = p.kv_slot ? p.kv_slot[b] : b;
+            const int nk = p.self_rows + (p.kv_len ? p.kv_len[slot] : p.S_max);
+            const int nk16 = (nk + 15) & ~15;
+            const bool weighted = p.attn_w != nullptr && b < p.w_batch && p.n_w > 0;
+            const int w_start = nk - p.n_w;
+            for (int qt = 0; qt < p.n_qt; ++qt, ++it) {
+                const int sb = it % p.nsb, pb = it % p.npb;
+                const bool rows_here = qt * TC_QT + wq * 16 < p.P;         // warp-uniform: any real query in this warp's 16 rows
+                ptx::mbar_wait(bar(BAR_SF + sb), ((uint32_t)(it / p.nsb)) & 1u);
+                ptx::tc_fence_after();
+                const uint32_t ts = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(sb * p.n1);
+                float m = -INFINITY;
+                if (rows_here) {
+                    for (int c0 = 0; c0 < nk; c0 += 32) {
+                        float v[32];
+                        ptx::tmem_ld_32x32(ts + (uint32_t)c0, v);
+                        if (c0 + 32 <= nk) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) m = (c0 + j < nk) ? fmaxf(m, v[j]) : m;
+                        }
+                    }
+                }
+                ptx::mbar_wait(bar(BAR_PE + pb), (((uint32_t)(it / p.npb)) & 1u) ^ 1u);     // the P buffer is free again
+                float l = 0.f;
+                if (rows_here) {
+                    const float msc = m * p.scale_log2;
+                    uint8_t* prow = smem_gen + p.off_p + (size_t)pb * p.p_bytes + (size_t)row * 128;
+                    for (int c0 = 0; c0 < nk16; c0 += 32) {
+                        float v[32];
+                        ptx::tmem_ld_32x32(ts + (uint32_t)c0, v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float e = exp2f(fmaf(v[j], p.scale_log2, -msc));
+                            v[j] = (c0 + j < nk) ? e : 0.f;
+                            l += v[j];
+                        }
+                        if (weighted) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int kj = c0 + j;
+                                if (kj >= w_start && kj < nk) v[j] *= p.attn_w[kj - w_start];
+                            }
+                        }
+                        if (lane_ok) {
+                            uint8_t* atom = prow + (size_t)(c0 >> 6) * 8192;
+                            const int ck0 = (c0 & 63) >> 3;      // first 16-byte chunk (8 keys) of this 32-key group inside the atom
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 pk;
+                                pk.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
+                                pk.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
+                                *reinterpret_cast<uint4*>(atom + (((ck0 + g) ^ (row & 7)) << 4)) = pk;
+                            }
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                if (lane_ok) invl[(it & 3) * TC_QT + row] = 1.0f / l;
+                ptx::fence_proxy_async_smem();          // P (generic-proxy stores) must be visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::mbar_arrive(bar(BAR_SE + sb));
+                    ptx::mbar_arrive(bar(BAR_PF + pb));
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== epilogue: O (TMEM) / rowsum -> fp16 -> global =====================
+        const int wq = warp & 3;
+        const int row = wq * 16 + lane;
+        int it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int b = u / p.nhead, h = u - b * p.nhead;
+            for (int qt = 0; qt < p.n_qt; ++qt, ++it) {
+                ptx::mbar_wait(bar(BAR_OF), ((uint32_t)it) & 1u);
+                ptx::tc_fence_after();
+                const int q = qt * TC_QT + row;
+                const bool rows_here = qt * TC_QT + wq * 16 < p.P;
+                if (rows_here) {
+                    const uint32_t to = tmem_base + ((uint32_t)(wq * 32) << 16) + col_o;
+                    const float inv = invl[(it & 3) * TC_QT + (lane < 16 ? row : wq * 16)];
+                    __half* dst = p.out + ((int64_t)b * p.P + q) * p.E + h * TC_HD;
+                    const bool st_ok = lane < 16 && q < p.P;
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        float v[32];
+                        ptx::tmem_ld_32x32(to + (uint32_t)c0, v);
+                        if (st_ok) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 pk;
+                                pk.x = pack_half2(v[g * 8 + 0] * inv, v[g * 8 + 1] * inv); pk.y = pack_half2(v[g * 8 + 2] * inv, v[g * 8 + 3] * inv);
+                                pk.z = pack_half2(v[g * 8 + 4] * inv, v[g * 8 + 5] * inv); pk.w = pack_half2(v[g * 8 + 6] * inv, v[g * 8 + 7] * inv);
+                                *reinterpret_cast<uint4*>(dst + c0 + g * 8) = pk;
+                            }
+                        }
+                    }
+                    float v[16];
+                    ptx::tmem_ld_32x16(to + 64u, v);
+                    if (st_ok) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            uint4 pk;
+                            pk.x = pack_half2(v[g * 8 + 0] * inv, v[g * 8 + 1] * inv); pk.y = pack_half2(v[g * 8 + 2] * inv, v[g * 8 + 3] * inv);
+                            pk.z = pack_half2(v[g * 8 + 4] * inv, v[g * 8 + 5] * inv); pk.w = pack_half2(v[g * 8 + 6] * inv, v[g * 8 + 7] * inv);
+                            *reinterpret_cast<uint4*>(dst + 64 + g * 8) = pk;
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(bar(BAR_OE));
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+struct TmapKey {
+    const void* ptr;
+    int64_t rows, cols;
+    int box_cols, box_rows;
+    bool operator<(const TmapKey& o) const {
+        return std::tie(ptr, rows, cols, box_cols, box_rows) < std::tie(o.ptr, o.rows, o.cols, o.box_cols, o.box_rows);
+    }
+};
+
+// tensor maps are pure functions of (pointer, shape, box): the model's workspace is bump-allocated identically every call, so
+// a small cache removes the driver call from all but the first launches
+int cached_tmap(const void* ptr, int64_t rows, int64_t cols, int box_cols, int box_rows, CUtensorMap* out) {
+    static std::map<TmapKey, CUtensorMap> cache;
+    static std::mutex mu;
+    const TmapKey key{ptr, rows, cols, box_cols, box_rows};
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        if (cache.size() > 4096) cache.clear();
+        CUtensorMap tm;
+        PB_TRY(make_tmap_f16_2d_box(&tm, ptr, rows, cols, cols, box_cols, box_rows, box_cols == 64 ? 128 : 32));
+        it = cache.emplace(key, tm).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+}  // namespace
+
+// returns 0 = launched, 1 = error, -1 = shape not handled by this kernel (caller falls back to the mma.sync kernel)
+int launch_attention_tc(const AttnParams& a, cudaStream_t st) {
+    static const bool off = getenv("PB200_ATTN_LEGACY") != nullptr;      // A/B knob
+    if (off) return -1;
+    if (a.nhead <= 0 || a.E != a.nhead * TC_HD) return -1;
+    if (!(a.P % 16 == 0 && (a.P <= TC_QT || a.P % TC_QT == 0))) return -1;
+    if (a.S_max < 1 || ((uintptr_t)a.qkv & 15) || ((uintptr_t)a.ckv & 15) || ((uintptr_t)a.out & 15)) return -1;
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = a.B; p.P = a.P; p.nhead = a.nhead; p.E = a.E; p.S_max = a.S_max;
+    p.n_qt = (a.P + TC_QT - 1) / TC_QT;
+    p.self_rows = a.self_attn ? a.P : 0;
+    if (p.self_rows > 256) return -1;
+    p.n1 = (p.self_rows + a.S_max + 15) & ~15;
+    p.sbox = p.n1 - p.self_rows;
+    if (p.sbox > 256 || p.n1 + TC_O_COLS > 512 || (p.n1 > 256 && p.n1 - 256 < 16)) return -1;
+    p.kv_len = a.kv_len; p.kv_slot = a.kv_slot; p.scale_log2 = a.scale_log2;
+    p.attn_w = a.attn_w; p.n_w = a.attn_w ? a.n_w : 0; p.w_batch = a.w_batch; p.out = a.out;
+    p.k64_bytes = (uint32_t)p.n1 * 128u;
+    p.k16_bytes = (uint32_t)p.n1 * 32u;
+    p.kv_bytes = 2 * (p.k64_bytes + p.k16_bytes);          // n1 * 320: a multiple of 1024 since n1 % 16 == 0
+    p.p_bytes = (uint32_t)((p.n1 + 63) / 64) * 8192u;
+    p.nsb = 2 * p.n1 + TC_O_COLS <= 512 ? 2 : 1;
+    // shared-memory plan: prefer two K/V stages (hides the load of the next unit), then two P buffers
+    const uint32_t fixed = 2 * Q_BYTES + 4 * TC_QT * 4 + 8 * (BAR_COUNT + 1) + 1024 /*alignment slack*/;
+    const uint32_t cap = 227 * 1024;
+    p.nkv = 2; p.npb = 2;
+    if (fixed + 2 * p.kv_bytes + 2 * p.p_bytes > cap) p.npb = 1;
+    if (fixed + 2 * p.kv_bytes + p.npb * p.p_bytes > cap) { p.nkv = 1; p.npb = 2; }
+    if (fixed + p.nkv * p.kv_bytes + p.npb * p.p_bytes > cap) p.npb = 1;
+    if (fixed + p.nkv * p.kv_bytes + p.npb * p.p_bytes > cap) return -1;
+    p.off_q = 0;
+    p.off_kv = 2 * Q_BYTES;                                  // 20480: 1024-aligned
+    p.off_p = p.off_kv + p.nkv * p.kv_bytes;
+    p.off_invl = p.off_p + p.npb * p.p_bytes;
+    p.off_bar = p.off_invl + 4 * TC_QT * 4;
+    const size_t smem = (size_t)p.off_bar + 8 * (BAR_COUNT + 1) + 1024;
+
+    if (a.B == 0 || a.P == 0) return 0;
+    const int64_t q_rows = (int64_t)a.B * a.P;
+    CUtensorMap tq64, tq16, ts64, ts16, tc64, tc16;
+    PB_TRY(cached_tmap(a.qkv, q_rows, 3 * (int64_t)a.E, 64, TC_QT, &tq64));
+    PB_TRY(cached_tmap(a.qkv, q_rows, 3 * (int64_t)a.E, 16, TC_QT, &tq16));
+    const int sr = p.self_rows ? p.self_rows : 8;
+    PB_TRY(cached_tmap(a.qkv, q_rows, 3 * (int64_t)a.E, 64, sr, &ts64));
+    PB_TRY(cached_tmap(a.qkv, q_rows, 3 * (int64_t)a.E, 16, sr, &ts16));
+    // the conditioning cache holds `slots` blocks of S_max rows; the row count only bounds the TMA (out-of-range rows read
+    // as zero): slots is not known here, so bound by the largest slot index the launch can touch
+    const int64_t c_rows = (int64_t)(a.n_slots > 0 ? a.n_slots : a.B) * a.S_max;
+    PB_TRY(cached_tmap(a.ckv, c_rows, 2 * (int64_t)a.E, 64, p.sbox, &tc64));
+    PB_TRY(cached_tmap(a.ckv, c_rows, 2 * (int64_t)a.E, 16, p.sbox, &tc16));
+
+    static DeviceOnce attr;
+    if (attr.first()) PB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // algorithmic bytes: q, self k/v, out once; conditioning k/v once per sample
+    ProfScope prof("attention_tc", 2.0 * ((double)a.B * a.P * 4.0 * a.E + (double)a.B * a.S_max * 2.0 * a.E), st);
+    const int units = a.B * a.nhead;
+    const int grid = units < sm_count() ? units : sm_count();
+    attention_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tq64, tq16, ts64, ts16, tc64, tc16, p);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace pb

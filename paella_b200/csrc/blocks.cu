@@ -110,11 +110,11 @@ int pb200_dwconv_ln(const float* x, const float* skip, const float* w_packed, co
 }
 
 int pb200_grn_f16(void* h16, int batch, int rows_per_sample, int n, const uint64_t* sqsum, uint64_t* sqsum_next,
-                  int zero_per_sample, const float* gamma, const float* beta, void* stream) {
-    PB_CHECK(h16 && sqsum && sqsum_next && gamma && beta, "grn_f16: null pointer");
+                  int zero_per_sample, const float* gamma, const float* beta, float* scale_scratch, void* stream) {
+    PB_CHECK(h16 && sqsum && sqsum_next && gamma && beta && scale_scratch, "grn_f16: null pointer");
     PB_CHECK(sqsum != sqsum_next, "grn_f16: the statistic being read and the one being zeroed must differ");
     return launch_grn_fused(reinterpret_cast<__half*>(h16), batch, rows_per_sample, n, sqsum, sqsum_next, zero_per_sample, gamma, beta,
-                            (cudaStream_t)stream);
+                            scale_scratch, (cudaStream_t)stream);
 }
 
 int pb200_grn_f32(const float* x, int batch, int rows_per_sample, int n, const float* gamma, const float* beta, float* stat,

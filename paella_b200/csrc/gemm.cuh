@@ -27,6 +27,10 @@ struct GemmSmem {
 // box = 64 columns x box_rows rows, 128-byte swizzle, zero fill out of bounds.
 int make_tmap_f16_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
+// same with an explicit box (box_cols x box_rows) and swizzle span (128 or 32 bytes; box_cols * 2 <= swizzle_bytes)
+int make_tmap_f16_2d_box(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                         int swizzle_bytes);
+
 int make_tmap_f16_nd(CUtensorMap* tm, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes,
                      const int* box);
 

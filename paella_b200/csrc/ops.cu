@@ -432,88 +432,97 @@ int launch_dwconv_ln(const float* x, const float* skip, const float* w_packed, c
 }
 
 // ------------------------------------------------------------------ GlobalResponseNorm
-// One-kernel GRN: every CTA recomputes its sample's normaliser mean_n sqrt(sq[b,n]) (N fp32 values from L2), then
-// rescales its rows.  sq_next (the other half of a ping-pong pair) is zeroed for the next block's GEMM epilogue,
-// so the statistic buffer being read is never written in the same launch.
+// Two launches: (1) grn_scale_kernel, one CTA per sample: the normaliser mean_n sqrt(sq[b,n]) and the per-(sample, channel)
+// multiplier 1 + gamma[n] * Gx / (mean Gx + 1e-6) -> fp32 scale[b, n]; it also zeroes sq_next (the other half of the
+// ping-pong pair) for the next block's GEMM epilogue, so the statistic being read is never written in the same launch.
+// (2) grn_apply_kernel: a pure streaming pass h = h * scale[b, n] + beta[n] over the fp16 hidden with no per-CTA prologue
+// (the round-1 single kernel recomputed the N-term normaliser in EVERY CTA before its first load: 3.0 TB/s at 27 %
+// occupancy in ncu; the stream itself is now the only thing a CTA does).
 __device__ __forceinline__ float grn_fx(unsigned long long q) { return __ull2float_rn(q) * (1.0f / 16777216.0f); }
 
-__global__ void __launch_bounds__(384) grn_fused_kernel(__half* __restrict__ h, int P, int N, const unsigned long long* __restrict__ sq,
+__global__ void __launch_bounds__(512) grn_scale_kernel(int N, const unsigned long long* __restrict__ sq,
                                                         unsigned long long* __restrict__ sq_next, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, int rows_per_cta, int zero_per_sample) {
+                                                        float* __restrict__ scale, int zero_per_sample) {
     pdl_launch_dependents();
-    const int b = blockIdx.y;
+    const int b = blockIdx.x;
     const unsigned long long* sqb = sq + (int64_t)b * N;
     float s = 0.f;
     for (int i = threadIdx.x; i < (N >> 1); i += blockDim.x) {
         const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(sqb + 2 * i);
         s += sqrtf(grn_fx(q.x)) + sqrtf(grn_fx(q.y));
     }
-    __shared__ float red[12];
+    __shared__ float red[16];
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
     float tot = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
     const float inv_denom = 1.0f / (tot / N + 1e-6f);
-    if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < zero_per_sample; i += blockDim.x) sq_next[(int64_t)b * zero_per_sample + i] = 0ull;
-    const int r0 = blockIdx.x * rows_per_cta;
-    const int r1 = min(P, r0 + rows_per_cta);
-    __half* hb = h + ((int64_t)b * P) * N;
-    for (int ch = threadIdx.x; ch < (N >> 3); ch += blockDim.x) {
-        const int col = ch * 8;
-        float sc[8], be[8];
-        {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
-            const ulonglong2 u0 = *reinterpret_cast<const ulonglong2*>(sqb + col), u1 = *reinterpret_cast<const ulonglong2*>(sqb + col + 2);
-            const ulonglong2 u2 = *reinterpret_cast<const ulonglong2*>(sqb + col + 4), u3 = *reinterpret_cast<const ulonglong2*>(sqb + col + 6);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
-            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float qq[8] = {grn_fx(u0.x), grn_fx(u0.y), grn_fx(u1.x), grn_fx(u1.y), grn_fx(u2.x), grn_fx(u2.y), grn_fx(u3.x), grn_fx(u3.y)};
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        scale[(int64_t)b * N + i] = fmaf(__ldg(gamma + i), sqrtf(grn_fx(sqb[i])) * inv_denom, 1.0f);
+    for (int i = threadIdx.x; i < zero_per_sample; i += blockDim.x) sq_next[(int64_t)b * zero_per_sample + i] = 0ull;
+}
+
+// grid (column groups of 8 channels x GRN_TPB threads, row groups, samples); each thread owns 8 channels and walks
+// rows_per_cta rows with 8 independent 16-byte loads in flight
+constexpr int GRN_ROWS = 8;
+__global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ h, int P, int N, const float* __restrict__ scale,
+                                                        const float* __restrict__ beta, int rows_per_cta) {
+    pdl_launch_dependents();
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= (N >> 3)) return;
+    const int b = blockIdx.z, col = ch * 8;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(P, r0 + rows_per_cta);
+    __half* hb = h + ((int64_t)b * P) * N + col;
+    // issue the first row group's loads before the (L2-resident) scale / beta vectors are needed
+    uint4 v[GRN_ROWS];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                sc[j] = fmaf(gg[j], sqrtf(qq[j]) * inv_denom, 1.0f);
-                be[j] = bb[j];
-            }
-        }
-        for (int r = r0; r < r1; r += 8) {       // 8 independent 16-byte loads in flight per thread
-            uint4 v[8];
+    for (int u = 0; u < GRN_ROWS; ++u)
+        if (r0 + u < r1) v[u] = *reinterpret_cast<const uint4*>(hb + (int64_t)(r0 + u) * N);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)b * N + col)), s1 = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)b * N + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int r = r0; r < r1; r += GRN_ROWS) {
+        uint4 nx[GRN_ROWS];
+        const int rn = r + GRN_ROWS;
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (r + u < r1) v[u] = *reinterpret_cast<const uint4*>(hb + (int64_t)(r + u) * N + col);
+        for (int u = 0; u < GRN_ROWS; ++u)
+            if (rn + u < r1) nx[u] = *reinterpret_cast<const uint4*>(hb + (int64_t)(rn + u) * N);      // next group in flight
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (r + u < r1) {
-                    __half2* hv = reinterpret_cast<__half2*>(&v[u]);
+        for (int u = 0; u < GRN_ROWS; ++u) {
+            if (r + u < r1) {
+                __half2* hv = reinterpret_cast<__half2*>(&v[u]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = __half22float2(hv[j]);
-                        hv[j] = __floats2half2_rn(fmaf(f.x, sc[2 * j], be[2 * j]), fmaf(f.y, sc[2 * j + 1], be[2 * j + 1]));
-                    }
-                    *reinterpret_cast<uint4*>(hb + (int64_t)(r + u) * N + col) = v[u];
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(hv[j]);
+                    hv[j] = __floats2half2_rn(fmaf(f.x, sc[2 * j], be[2 * j]), fmaf(f.y, sc[2 * j + 1], be[2 * j + 1]));
                 }
+                *reinterpret_cast<uint4*>(hb + (int64_t)(r + u) * N) = v[u];
             }
         }
+#pragma unroll
+        for (int u = 0; u < GRN_ROWS; ++u) v[u] = nx[u];
     }
 }
 
 int launch_grn_fused(__half* h, int B, int P, int N, const uint64_t* sq, uint64_t* sq_next, int zero_per_sample, const float* gamma,
-                     const float* beta, cudaStream_t st) {
+                     const float* beta, float* scale_scratch, cudaStream_t st) {
     ProfScope prof("grn", (double)B * P * N * 4.0, st);
     PB_CHECK(N % 8 == 0, "grn: N=%d must be a multiple of 8", N);
+    PB_CHECK(scale_scratch != nullptr, "grn: scale scratch [B, N] fp32 required");
     if (B == 0 || P == 0) return 0;
-    // ~16 rows per CTA keeps the normaliser recomputation (N sqrt) small next to the rescale (rows * N); 8 when
-    // that would leave SMs idle.  The block size divides the N/8 column chunks evenly (N=5120 -> 2 per thread of 320,
-    // N=2560 -> 1): with a fixed 256 the last pass ran 25-50% full.
-    int rows_per_cta = P >= 16 ? 16 : P;
-    if ((int64_t)ceil_div(P, rows_per_cta) * B < 2 * sm_count() && rows_per_cta > 8) rows_per_cta = 8;
-    dim3 grid(ceil_div(P, rows_per_cta), B);
-    PB_CHECK(grid.y <= 65535, "grn: batch too large");
+    PB_CHECK(B <= 65535, "grn: batch too large");
+    grn_scale_kernel<<<B, 512, 0, st>>>(N, reinterpret_cast<const unsigned long long*>(sq), reinterpret_cast<unsigned long long*>(sq_next),
+                                       gamma, scale_scratch, zero_per_sample);
+    PB_LAUNCH_CHECK();
+    // rows per CTA: 16 (two 8-row groups, the second in flight while the first is converted), 8 when that leaves SMs idle
     const int nch = N >> 3;
-    const int threads = ceil_div(ceil_div(nch, ceil_div(nch, 384)), 32) * 32;
-    grn_fused_kernel<<<grid, threads, 0, st>>>(h, P, N, reinterpret_cast<const unsigned long long*>(sq),
-                                           reinterpret_cast<unsigned long long*>(sq_next), gamma, beta, rows_per_cta, zero_per_sample);
+    const int tpb = nch >= 256 ? 256 : ((nch + 31) / 32) * 32;
+    int rows_per_cta = P >= 16 ? 16 : P;
+    if ((int64_t)ceil_div(P, rows_per_cta) * B * ceil_div(nch, tpb) < 4 * sm_count() && rows_per_cta > 8) rows_per_cta = 8;
+    dim3 grid(ceil_div(nch, tpb), ceil_div(P, rows_per_cta), B);
+    grn_apply_kernel<<<grid, tpb, 0, st>>>(h, P, N, scale_scratch, beta, rows_per_cta);
     PB_LAUNCH_CHECK();
     return 0;
 }

@@ -22,10 +22,11 @@ int launch_ln_patchify2(const float* x, int B, int h, int w, int c, __half* out,
 int launch_dwconv_ln(const float* x, const float* skip, const float* w_packed, const float* bias, int B, int h, int w,
                      int c, int k, __half* out, cudaStream_t st);
 
-// GlobalResponseNorm in one launch: h[b,p,n] = h*(1 + gamma[n]*Gx[b,n]/(mean_n Gx + 1e-6)) + beta[n], Gx = sqrt(sq[b,n]);
-// zeroes all B*zero_per_sample floats of sq_next (the other buffer of a ping-pong pair) for the next block
+// GlobalResponseNorm: h[b,p,n] = h*(1 + gamma[n]*Gx[b,n]/(mean_n Gx + 1e-6)) + beta[n], Gx = sqrt(sq[b,n]) (2^-24 fixed point);
+// zeroes all B*zero_per_sample entries of sq_next (the other buffer of a ping-pong pair) for the next block.
+// scale_scratch: fp32 [B, N] (the per-sample multipliers, written by the first of the two launches)
 int launch_grn_fused(__half* h, int B, int P, int N, const uint64_t* sq, uint64_t* sq_next, int zero_per_sample, const float* gamma,
-                     const float* beta, cudaStream_t st);
+                     const float* beta, float* scale_scratch, cudaStream_t st);
 
 // gen_r_embedding: r [B] -> [B, c_r]
 int launch_r_embed(const float* r, int B, int c_r, float* out, cudaStream_t st);

@@ -376,6 +376,7 @@ struct FeatWs {
     float* xu[PB200_MAX_LEVELS];
     __half *a16, *h16, *qkv16, *o16;
     uint64_t *gsq, *gscale;      // GRN statistic ping/pong (2^-24 fixed point)
+    float* grn_mult;             // GRN per-(sample, channel) multipliers [Bt, 4*max_c]
     int64_t* lnstat;             // folded LayerNorm: per AttnBlock [M][2] fixed-point row statistics
     int64_t lnstat_stride;       // int64 elements per AttnBlock
     float* lnmean;               // per AttnBlock [M]: mean of its input rows (the next folded LayerNorm's per-row shift)
@@ -400,6 +401,7 @@ static void plan_features(const pb200_paella* m, int Bt, int H, int W, Arena& ar
     ws.o16 = ar.take<__half>(max_mc);
     ws.gsq = ar.take<uint64_t>((int64_t)Bt * 4 * m->max_c);     // ping
     ws.gscale = ar.take<uint64_t>((int64_t)Bt * 4 * m->max_c);  // pong (second GRN statistic buffer)
+    ws.grn_mult = ar.take<float>((int64_t)Bt * 4 * m->max_c);
     {
         int64_t max_m = 0;
         for (const BlockPlan& b : m->blocks)
@@ -717,7 +719,7 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
                 grn_flip ^= 1;
                 e1.sqsum = stat; e1.rows_per_sample = P;
                 PB_TRY(m->gemm(ws.a16, ch, M, ch, b.w1, 4 * (int64_t)ch, e1, st));
-                PB_TRY(launch_grn_fused(ws.h16, Bc, P, 4 * ch, stat, stat_next, 4 * m->max_c, m->w<float>(b.gamma), m->w<float>(b.beta), st));
+                PB_TRY(launch_grn_fused(ws.h16, Bc, P, 4 * ch, stat, stat_next, 4 * m->max_c, m->w<float>(b.gamma), m->w<float>(b.beta), ws.grn_mult, st));
                 // the next AttnBlock's LayerNorm is folded into its QKV GEMM when this block feeds it directly
                 const bool fold = b.ln_fold_attn >= 0;
                 pb200_gemm_epilogue e2 = epi(fold ? PB200_EPI_RESID_LN_F32 : PB200_EPI_RESID_F32, m->w<float>(b.b2), x, ch);
@@ -754,6 +756,7 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
                 ap.ckv = reinterpret_cast<const __half*>(cache + cond_block_off(m, b.attn_index, cache_slots, s_max));
                 ap.kv_len = kv_len;
                 ap.kv_slot = kv_slot;
+                ap.n_slots = cache_slots;
                 ap.out = ws.o16;
                 ap.B = Bt; ap.P = P; ap.S_max = s_max; ap.E = ch; ap.nhead = c.nhead[l];
                 ap.self_attn = c.self_attn;

@@ -203,6 +203,38 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64): 2 = SWIZZLE_128B, 6 = SWIZZLE_32B).  All tiles here are dense
+// [rows][128 B] or [rows][32 B] as TMA writes them:
+//   K-major  (rows = M/N index, the row holds K):    8-row groups are SBO = 8 * row bytes apart
+//   MN-major (rows = K index, the row holds M/N):    8-row (K) groups are SBO = 8 * row bytes apart; one row = one MN block
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                           // LBO (unused by the dense single-block tiles above)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) { return umma_desc(smem_addr, 1024, 2); }
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) { return umma_desc(smem_addr, 256, 6); }
+
 // Shared-memory matrix descriptor for a K-major operand tile stored as rows of 128 bytes
 // (64 fp16) with the 128-byte swizzle TMA writes (CU_TENSOR_MAP_SWIZZLE_128B):
 //   start address >>4 | LBO (unused for swizzled K-major) | SBO = 8 rows * 128 B = 1024 | version 1 | SWIZZLE_128B
@@ -213,6 +245,12 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
+}
+
+// Instruction descriptor with explicit operand major-ness (0 = K-major, 1 = MN-major), fp16 inputs, fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_f16_major(int m, int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
 }
 
 // Instruction descriptor, kind::f16: D fp32, A/B fp16 (fmt 0) or bf16 (fmt 1), both K-major, M x N tile.

@@ -358,6 +358,23 @@ static void conv_tile(int gw, int& tw, int& th) {
 
 }  // namespace pb
 
+namespace pb {
+// Images per pass through the codec.  All of one pass's activations (x, LayerNorm scratch, fp16 operands, the 4c-wide MLP
+// hidden: ~28 MB per 256x256 image at the bottleneck) should stay L2-resident from the kernel that writes them to the kernel
+// that reads them; a whole batch streams every intermediate through HBM instead.  PB200_VQ_SUBBATCH overrides (0 = whole batch).
+static int vq_sub_batch(int batch, int img_h, int img_w) {
+    static const char* env = getenv("PB200_VQ_SUBBATCH");
+    int n = env ? atoi(env) : -1;
+    if (n < 0) {
+        const double per_img = (double)(img_h / 4) * (img_w / 4) * 7168.0;      // bytes of bottleneck activations per image
+        n = (int)(96.0e6 / per_img);
+        if (n < 1) n = 1;
+    }
+    return (n == 0 || n > batch) ? batch : n;
+}
+
+}  // namespace pb
+
 extern "C" {
 
 int64_t pb200_vqgan_resblock_workspace_bytes(int batch, int h, int w, int c) {
@@ -476,10 +493,26 @@ int64_t pb200_vqgan_workspace_bytes(const pb200_vqgan* m, int batch, int img_h, 
     return off + 256;
 }
 
+static int vq_encode_pass(pb200_vqgan* m, const float* img, int batch, int img_h, int img_w, float* latents_nchw,
+                          float* quantised_nchw, int64_t* indices, void* workspace, int64_t workspace_bytes, void* stream);
+
 int pb200_vqgan_encode(pb200_vqgan* m, const float* img, int batch, int img_h, int img_w, float* latents_nchw,
                        float* quantised_nchw, int64_t* indices, void* workspace, int64_t workspace_bytes, void* stream) {
     PB_CHECK(m->blob != nullptr, "encode: weights not bound");
     if (m->host_params_stale) PB_TRY(pb200_vqgan_sync_params(m, stream));
+    const int sub = vq_sub_batch(batch, img_h, img_w);
+    const int64_t lat = (int64_t)m->cfg.c_latent * (img_h / 4) * (img_w / 4);
+    for (int b0 = 0; b0 < batch; b0 += sub) {
+        const int nb = batch - b0 < sub ? batch - b0 : sub;
+        PB_TRY(vq_encode_pass(m, img + (int64_t)b0 * 3 * img_h * img_w, nb, img_h, img_w, latents_nchw ? latents_nchw + b0 * lat : nullptr,
+                              quantised_nchw ? quantised_nchw + b0 * lat : nullptr,
+                              indices ? indices + (int64_t)b0 * (img_h / 4) * (img_w / 4) : nullptr, workspace, workspace_bytes, stream));
+    }
+    return 0;
+}
+
+static int vq_encode_pass(pb200_vqgan* m, const float* img, int batch, int img_h, int img_w, float* latents_nchw,
+                          float* quantised_nchw, int64_t* indices, void* workspace, int64_t workspace_bytes, void* stream) {
     PB_CHECK(img_h % 4 == 0 && img_w % 4 == 0, "encode: image %dx%d not divisible by 4", img_h, img_w);
     PB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -542,11 +575,29 @@ int pb200_vqgan_decode(pb200_vqgan* m, const int64_t* indices, const float* late
     return pb200_vqgan_decode_ex(m, indices, latents_nchw, batch, h, w, img, PB200_IMG_F32_NCHW, workspace, workspace_bytes, stream);
 }
 
+static int vq_decode_pass(pb200_vqgan* m, const int64_t* indices, const float* latents_nchw, int batch, int h, int w, void* img,
+                          int img_mode, void* workspace, int64_t workspace_bytes, void* stream);
+
 int pb200_vqgan_decode_ex(pb200_vqgan* m, const int64_t* indices, const float* latents_nchw, int batch, int h, int w, void* img,
                           int img_mode, void* workspace, int64_t workspace_bytes, void* stream) {
     PB_CHECK(m->blob != nullptr, "decode: weights not bound");
     PB_CHECK(img_mode >= 0 && img_mode <= 2, "decode: unknown image mode %d", img_mode);
     if (m->host_params_stale) PB_TRY(pb200_vqgan_sync_params(m, stream));
+    const int sub = vq_sub_batch(batch, 4 * h, 4 * w);
+    const int64_t px = (int64_t)16 * h * w * 3;          // output elements per image
+    for (int b0 = 0; b0 < batch; b0 += sub) {
+        const int nb = batch - b0 < sub ? batch - b0 : sub;
+        void* out = img_mode == PB200_IMG_U8_NHWC ? (void*)(reinterpret_cast<uint8_t*>(img) + b0 * px)
+                                                  : (void*)(reinterpret_cast<float*>(img) + b0 * px);
+        PB_TRY(vq_decode_pass(m, indices ? indices + (int64_t)b0 * h * w : nullptr,
+                              latents_nchw ? latents_nchw + (int64_t)b0 * m->cfg.c_latent * h * w : nullptr, nb, h, w, out, img_mode,
+                              workspace, workspace_bytes, stream));
+    }
+    return 0;
+}
+
+static int vq_decode_pass(pb200_vqgan* m, const int64_t* indices, const float* latents_nchw, int batch, int h, int w, void* img,
+                          int img_mode, void* workspace, int64_t workspace_bytes, void* stream) {
     PB_CHECK((indices != nullptr) != (latents_nchw != nullptr), "decode: pass indices or latents, not both");
     PB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;

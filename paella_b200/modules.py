@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -92,8 +93,9 @@ def _mlp_rows(mlp: nn.Sequential, a16: torch.Tensor, resid_rows: torch.Tensor, b
     h16 = torch.empty(M, n, dtype=torch.float16, device=a16.device)
     sq = torch.zeros(2, batch, n, dtype=torch.int64, device=a16.device)
     ops.gemm_f16(a16, _w16(lin1, "w16", lin1.weight), _lib.EPI_GELU_F16, h16, bias=_f32(lin1.bias), sqsum=sq[0], rows_per_sample=P)
+    mult = torch.empty(batch, n, dtype=torch.float32, device=a16.device)
     check(lib().pb200_grn_f16(ptr(h16), batch, P, n, ptr(sq[0]), ptr(sq[1]), n, ptr(_f32(grn.gamma).view(-1)),
-                              ptr(_f32(grn.beta).view(-1)), current_stream()), "pb200_grn_f16")
+                              ptr(_f32(grn.beta).view(-1)), ptr(mult), current_stream()), "pb200_grn_f16")
     ops.gemm_f16(h16, _w16(lin2, "w16", lin2.weight), _lib.EPI_RESID_F32, resid_rows, bias=_f32(lin2.bias), resid=resid_rows)
     return resid_rows
 
@@ -257,6 +259,11 @@ class TimestepBlock(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
+# A/B knob: run guided steps in groups of this many (cond, uncond) pairs so that a block's activations stay L2-resident
+# (0 = whole batch at once).  See Paella._features_chunked.
+_SUBBATCH_PAIRS = int(os.environ.get("PB200_SUBBATCH", "0") or 0)
+
+
 class ConditioningCache:
     """x- and t-independent conditioning work of one sample() call: c_embed and every AttnBlock's
     cond K/V for ``batch_total`` samples (conditional rows first, then unconditional rows)."""
@@ -513,7 +520,9 @@ class Paella(nn.Module):
         shared = [uniform(g) for g in groups]
         slots = sum(1 if sh else g["byt5"].shape[0] for g, sh in zip(groups, shared))
         with torch.cuda.device(dev):
-            cache = torch.empty(L.pb200_paella_cond_cache_bytes(self._handle, slots, s_max), dtype=torch.uint8, device=dev)
+            # zero-filled: rows between a slot's own length and s_max are never written by the K/V GEMMs, and the attention
+            # kernel multiplies them by exactly-zero probabilities -- they must be finite
+            cache = torch.zeros(L.pb200_paella_cond_cache_bytes(self._handle, slots, s_max), dtype=torch.uint8, device=dev)
             ws = self._ws(L.pb200_paella_workspace_bytes(self._handle, bt, latent_hw[0], latent_hw[1], s_max))
             off = 0
             keep = []
@@ -604,6 +613,9 @@ class Paella(nn.Module):
             Bt *= 2
         if Bt != cond.batch_total:
             raise PaellaB200Error(f"batch {Bt} does not match the conditioning cache ({cond.batch_total})")
+        chunk = _SUBBATCH_PAIRS if cfg_pairs else 0
+        if chunk and x.shape[0] > chunk:
+            return self._features_chunked(x, r, cond, attn_weights, attn_weights_batch, chunk)
         with torch.cuda.device(dev):
             x = x.to(device=dev, dtype=torch.int64).contiguous()
             r = r.to(device=dev, dtype=torch.float32).contiguous()
@@ -615,6 +627,30 @@ class Paella(nn.Module):
                                           aw.numel() if aw is not None else 0, attn_weights_batch, ptr(feats), ptr(ws),
                                           ws.numel(), current_stream()), "pb200_paella_features")
         return feats
+
+    def _features_chunked(self, x, r, cond: ConditioningCache, attn_weights, attn_weights_batch, chunk: int) -> torch.Tensor:
+        """The CFG batch in groups of ``chunk`` (cond, uncond) pairs, each group through the whole denoiser on its own.  Samples
+        are independent, so this is the same arithmetic; the point is the working set: at 2 x 64 samples one level-1 block
+        touches x 42 MB + hidden 84 MB + qkv 63 MB, more than the 126 MB L2, so every kernel re-reads its input from HBM;
+        half the batch keeps a block's tensors L2-resident from the kernel that writes them to the one that reads them."""
+        dev = self._device()
+        B, H, W = x.shape
+        n_tok = H * W
+        full = torch.empty(2 * B * n_tok, self._cfg["c_out"], dtype=torch.float32, device=dev)
+        maps = cond.__dict__.setdefault("_chunk_maps", {})
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            key = (lo, hi, B)
+            if key not in maps:
+                base = cond.slot_map if cond.slot_map is not None else torch.arange(2 * B, dtype=torch.int32, device=dev)
+                maps[key] = torch.cat([base[lo:hi], base[B + lo:B + hi]]).contiguous()
+            sub = ConditioningCache(cond.cache, 2 * (hi - lo), cond.s_max, cond.slots, maps[key])
+            aw_b = max(0, min(attn_weights_batch, hi) - lo) if attn_weights is not None else 0
+            f = self.features(x[lo:hi], r[lo:hi], sub, attn_weights, aw_b, cfg_pairs=True)
+            n = (hi - lo) * n_tok
+            full[lo * n_tok:hi * n_tok] = f[:n]
+            full[(B + lo) * n_tok:(B + hi) * n_tok] = f[n:]
+        return full
 
     def logits_from_features(self, feats: torch.Tensor, batch: int, h: int, w: int) -> torch.Tensor:
         L = lib()

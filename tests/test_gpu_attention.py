@@ -1,0 +1,99 @@
+"""Attention core (ref/src/modules.py:12-19, ref/utils/alter_attention.py:19-36) through the C ABI (pb200_attention) against an
+fp32 torch restatement on the same fp16-rounded q/k/v: the tcgen05/TMEM kernel (head_dim 80, csrc/attention_tc.cu) on the
+shapes of BASELINE configs 2 and 4, the mma.sync kernel on everything else, and the two kernels against each other."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _log(payload):
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "attention_parity.jsonl"), "a") as f:
+        f.write(json.dumps(payload) + "\n")
+
+
+def _reference(qkv, ckv, kv_len, B, P, S, E, H, self_attn, aw):
+    hd = E // H
+    q = qkv[:, :E].float().view(B, P, H, hd).permute(0, 2, 1, 3)
+    ks = qkv[:, E:2 * E].float().view(B, P, H, hd).permute(0, 2, 1, 3)
+    vs = qkv[:, 2 * E:].float().view(B, P, H, hd).permute(0, 2, 1, 3)
+    kc = ckv[:, :, :E].float().view(B, S, H, hd).permute(0, 2, 1, 3)
+    vc = ckv[:, :, E:].float().view(B, S, H, hd).permute(0, 2, 1, 3)
+    out = torch.empty(B, H, P, hd, device=qkv.device)
+    for b in range(B):
+        n = int(kv_len[b]) if kv_len is not None else S
+        k = torch.cat([ks[b], kc[b, :, :n]], dim=1) if self_attn else kc[b, :, :n]
+        v = torch.cat([vs[b], vc[b, :, :n]], dim=1) if self_attn else vc[b, :, :n]
+        w = torch.softmax(q[b] @ k.transpose(1, 2) / hd ** 0.5, dim=-1)
+        if aw is not None:
+            w = w.clone()
+            w[:, :, -aw.numel():] *= aw
+        out[b] = w @ v
+    return out.permute(0, 2, 1, 3).reshape(B * P, E)
+
+
+def _run(B, P, S, H, hd, self_attn, varlen, weighted, seed=0):
+    from paella_b200 import _lib
+    L = _lib.lib()
+    E = H * hd
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    qkv = (torch.randn(B * P, 3 * E, device=DEV, generator=g) * 1.5).half()
+    ckv = (torch.randn(B, S, 2 * E, device=DEV, generator=g) * 1.5).half()
+    kv_len = None
+    if varlen:
+        kv_len = torch.randint(max(1, S // 2), S + 1, (B,), device=DEV, generator=g, dtype=torch.int32)
+        kv_len[0] = S
+        for b in range(B):          # rows past a sample's length hold junk the kernel must ignore (finite, as the model guarantees)
+            ckv[b, int(kv_len[b]):] = 777.0
+    aw = (torch.rand(5, device=DEV, generator=g) * 2).float() if weighted else None
+    out = torch.full((B * P, E), float("nan"), device=DEV, dtype=torch.float16)
+    _lib.check(L.pb200_attention(_lib.ptr(qkv), _lib.ptr(ckv), _lib.ptr(kv_len), _lib.ptr(out), B, P, S, E, H, int(self_attn),
+                                 _lib.ptr(aw), 5 if weighted else 0, B, _lib.current_stream()), "pb200_attention")
+    torch.cuda.synchronize()
+    want = _reference(qkv, ckv, kv_len, B, P, S, E, H, self_attn, aw)
+    d = out.float() - want
+    return float(d.abs().max()), float(d.pow(2).mean().sqrt()), out
+
+
+# (B, P, S, heads, head_dim, self_attn, varlen, weighted)
+TC_CASES = [
+    (4, 64, 132, 16, 80, True, False, False),      # BASELINE config 2, level 1: 196 keys, 2 S accumulators, 2 K/V stages
+    (3, 16, 132, 16, 80, True, True, False),       # config 2, level 2: 16 queries in a 64-row tile
+    (2, 256, 136, 16, 80, True, True, False),      # config 4, level 1: 4 query tiles per unit, 392 keys (N split 256 + 144)
+    (2, 64, 136, 16, 80, True, False, True),       # config 4, level 2 + attn_weights
+    (5, 64, 20, 4, 80, False, True, False),        # cross-attention only, short ragged conditioning
+    (2, 128, 7, 2, 80, True, False, False),        # two query tiles, odd conditioning length
+    (160, 64, 132, 16, 80, True, False, False),    # more units than SMs: every CTA walks several units (ring wrap-around)
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tcgen05_attention_vs_fp32_reference(case):
+    mx, rms, _ = _run(*case)
+    _log({"kernel": "tcgen05", "case": case, "max_abs": mx, "rms": rms})
+    assert mx < 4e-3 and rms < 4e-4, (case, mx, rms)      # outputs are O(1): fp16 P and fp16 output rounding
+
+
+@pytest.mark.parametrize("case", [(2, 64, 9, 4, 16, True, False, False), (2, 16, 20, 4, 32, True, True, True),
+                                  (2, 100, 30, 2, 64, True, False, False), (3, 64, 132, 16, 80, True, True, False)])
+def test_mma_sync_attention_vs_fp32_reference(case):
+    """Other head dims / query counts run the mma.sync kernel; with PB200_ATTN_LEGACY=1 (child process) so does head_dim 80."""
+    if case[4] == 80:
+        code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_attention as t; "
+                "mx, rms, _ = t._run(*%r); print(mx, rms)") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                               os.path.dirname(os.path.abspath(__file__)), case)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PB200_ATTN_LEGACY="1"))
+        assert r.returncode == 0, r.stderr[-2000:]
+        mx, rms = (float(x) for x in r.stdout.split()[-2:])
+    else:
+        mx, rms, _ = _run(*case)
+    _log({"kernel": "mma.sync", "case": case, "max_abs": mx, "rms": rms})
+    assert mx < 4e-3 and rms < 4e-4, (case, mx, rms)
