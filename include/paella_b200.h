@@ -133,6 +133,11 @@ typedef struct pb200_gemm_epilogue {
     int ln_c;                  /* F16_LN: number of columns the statistics cover (= K of this GEMM) */
     const float* ln_shift;     /* RESID_LN / F16_LN: fp32 [M] per-row shift the producer subtracted, or NULL (= 0) */
     float* ln_mean_out;        /* F16_LN: fp32 [M] true row mean (shift + mean of the shifted row), or NULL */
+    const void* a_scale;       /* RESID / RESID_LN: fp16 [M / rows_per_sample, a_scale_ld] per-(sample, k) factors multiplied into
+                                  the A operand on its way to the tensor core (GlobalResponseNorm folded into the GEMM that
+                                  consumes it: A'[m,k] = A[m,k] * a_scale[m / rows_per_sample, k]), or NULL.  Needs M > 128,
+                                  K % 64 == 0 and rows_per_sample dividing 128 (>= 16) or a multiple of 128 */
+    int64_t a_scale_ld;
 } pb200_gemm_epilogue;
 
 int pb200_gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t m, int64_t n, int64_t k,

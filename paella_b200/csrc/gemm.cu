@@ -70,15 +70,16 @@ int make_tmap_f16_2d_box(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t
     PB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
     PB_CHECK(((uintptr_t)ptr & 15) == 0, "TMA: base pointer must be 16-byte aligned");
     PB_CHECK((ld * 2) % 16 == 0, "TMA: row stride %lld halves is not a multiple of 16 bytes", (long long)ld);
-    PB_CHECK(box_rows >= 1 && box_rows <= 256 && box_cols >= 8 && box_cols * 2 <= swizzle_bytes, "TMA: bad box %dx%d for swizzle %d",
-             box_rows, box_cols, swizzle_bytes);
-    PB_CHECK(swizzle_bytes == 128 || swizzle_bytes == 32, "TMA: swizzle %d unsupported", swizzle_bytes);
+    PB_CHECK(swizzle_bytes == 128 || swizzle_bytes == 32 || swizzle_bytes == 0, "TMA: swizzle %d unsupported", swizzle_bytes);
+    PB_CHECK(box_rows >= 1 && box_rows <= 256 && box_cols >= 8 && (swizzle_bytes == 0 ? box_cols <= 256 : box_cols * 2 <= swizzle_bytes),
+             "TMA: bad box %dx%d for swizzle %d", box_rows, box_cols, swizzle_bytes);
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(box %dx%d, swizzle %d) failed (%d)", box_rows, box_cols, swizzle_bytes, (int)r);
     return 0;
@@ -635,14 +636,22 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 //   empty[s]  (each CTA): tcgen05.commit.cta_group::2 multicast from the leader's MMA thread
 //   tfull[a]  (each CTA): same commit, when a tile's last k-block has been issued
 //   tempty[a] (leader)  : one arrival per epilogue warp of BOTH CTAs (the peer arrives remotely)
-template <int BLOCK_N, int MODE>
-__global__ void __launch_bounds__(gemm_threads(BLOCK_N), 1)
+// ASCALE (GlobalResponseNorm folded into the A operand, ref/src/modules.py:37-40 + :53): the A tile is multiplied in shared
+// memory, between TMA and MMA, by a per-(sample, k) fp16 factor  s[b, k] = 1 + gamma[k] * Nx[b, k]  -- GEMM2 of a ResBlock then
+// computes (h * s) W2^T + (W2 beta + b2) = GRN(h) W2^T + b2 without the separate read-modify-write pass over the 4c-wide hidden.
+// Two extra warps per CTA (64 threads, two rows each) transform every stage: the A tile and the [samples x 64] slice of s land on
+// a CTA-local barrier (afull), the transform warps rescale the swizzled rows in place, fence the generic->async proxy and arrive
+// on the leader's ready[s]; the MMA thread waits for full[s] (both W halves) and ready[s] (both CTAs' A tiles transformed).
+constexpr int GEMM_ASCALE_WARPS = 2;
+constexpr int GEMM_ASCALE_BYTES = 1024;        // up to 8 samples x 64 factors per 128-row tile and k-block
+template <int BLOCK_N, int MODE, bool ASCALE>
+__global__ void __launch_bounds__(gemm_threads(BLOCK_N) + (ASCALE ? 32 * GEMM_ASCALE_WARPS : 0), 1)
 gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    const __grid_constant__ CUtensorMap tm_b_tail, const pb200_gemm_epilogue ep, int M, int N, int K,
-                    int n_main, int tail_bn) {
+                    const __grid_constant__ CUtensorMap tm_b_tail, const __grid_constant__ CUtensorMap tm_s,
+                    const pb200_gemm_epilogue ep, int M, int N, int K, int n_main, int tail_bn) {
     constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
     constexpr int BH_BYTES = (BLOCK_N / 2) * GEMM_BLOCK_K * 2;       // this CTA's half of the W tile
-    constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
+    constexpr int STAGE_BYTES = A_BYTES + BH_BYTES + (ASCALE ? GEMM_ASCALE_BYTES : 0);
     constexpr int STAGES = BLOCK_N >= 256 ? 6 : 8;
     constexpr int TMEM_COLS = BLOCK_N >= 256 ? 512 : 256;
     constexpr int EW = gemm_epi_warps(BLOCK_N);
@@ -653,6 +662,8 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    auto afull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 6 + s); };          // ASCALE: this CTA's A + factors landed
+    auto ready_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + 6 + s); };          // ASCALE (leader): both A tiles rescaled
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -702,6 +713,12 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 ptx::mbar_init(tfull_bar(s), 1);
                 ptx::mbar_init(tempty_bar(s), 2 * EW);
             }
+            if (ASCALE) {
+                for (int s = 0; s < STAGES; ++s) {
+                    ptx::mbar_init(afull_bar(s), 1);
+                    ptx::mbar_init(ready_bar(s), 2 * GEMM_ASCALE_WARPS);
+                }
+            }
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -730,14 +747,22 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 const int m_idx = un.m_pair * (2 * GEMM_BLOCK_M) + (int)crank * GEMM_BLOCK_M;
                 const int n_idx = un.n0 + (int)crank * (un.width / 2);
                 const bool narrow = un.width != BLOCK_N;
-                const uint32_t tx = 2u * (uint32_t)(A_BYTES + (un.width / 2) * GEMM_BLOCK_K * 2);
+                const uint32_t tx = 2u * (uint32_t)((ASCALE ? 0 : A_BYTES) + (un.width / 2) * GEMM_BLOCK_K * 2);
+                const int P = ep.rows_per_sample;
+                const int ns = ASCALE ? (P >= GEMM_BLOCK_M ? 1 : GEMM_BLOCK_M / P) : 0;      // samples in this CTA's 128 rows
                 for (int kb = 0; kb < n_kb; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t lfull = leader_full0 + 8u * stage;
                     if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), tx);
                     else ptx::mbar_arrive_cluster(lfull);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                    ptx::tma_load_2d_cg2(&tm_a, lfull, sa, kb * GEMM_BLOCK_K, m_idx);
+                    if (ASCALE) {       // A and its factors complete on this CTA's own barrier: the transform warps wait there
+                        ptx::mbar_arrive_expect_tx(afull_bar(stage), (uint32_t)(A_BYTES + ns * GEMM_BLOCK_K * 2));
+                        ptx::tma_load_2d(&tm_a, afull_bar(stage), sa, kb * GEMM_BLOCK_K, m_idx);
+                        ptx::tma_load_2d(&tm_s, afull_bar(stage), sa + A_BYTES + BH_BYTES, kb * GEMM_BLOCK_K, m_idx / P);
+                    } else {
+                        ptx::tma_load_2d_cg2(&tm_a, lfull, sa, kb * GEMM_BLOCK_K, m_idx);
+                    }
                     ptx::tma_load_2d_cg2(narrow ? &tm_b_tail : &tm_b, lfull, sa + A_BYTES, kb * GEMM_BLOCK_K, n_idx);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -762,6 +787,7 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 const uint32_t tmem_d = tmem_base + as * BLOCK_N;
                 for (int kb = 0; kb < n_kb; ++kb) {
                     ptx::mbar_wait(full_bar(stage), phase);
+                    if (ASCALE) ptx::mbar_wait(ready_bar(stage), phase);
                     ptx::tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -779,7 +805,55 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 ++iter;
             }
         }
-    } else {
+    } else if (ASCALE && warp >= 2 + EW) {
+        // ===================== A-operand transform (both CTAs, own 128 rows) =====================
+        const int t = (warp - 2 - EW) * 32 + lane;          // 0..63: rows t and t + 64 of the tile
+        const int P = ep.rows_per_sample;
+        const int ns = P >= GEMM_BLOCK_M ? 1 : GEMM_BLOCK_M / P;
+        const uint32_t leader_ready0 = ptx::mapa(ready_bar(0), 0);
+        uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int unit = unit0; unit < n_units; unit += unit_step) {
+            const Unit un = decode(unit);
+            if (un.width == 0) continue;
+            int sl[2];                                           // factor row (sample inside the tile) of this thread's two rows
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = t + 64 * i;
+                sl[i] = P >= GEMM_BLOCK_M ? 0 : min(r / P, ns - 1);
+            }
+            for (int kb = 0; kb < n_kb; ++kb) {
+                ptx::mbar_wait(afull_bar(stage), phase);
+                uint8_t* sa = smem_gen + stage * STAGE_BYTES;
+                const uint8_t* sc = sa + A_BYTES + BH_BYTES;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int r = t + 64 * i;
+                    uint4* arow = reinterpret_cast<uint4*>(sa + r * 128);
+                    const uint4* srow = reinterpret_cast<const uint4*>(sc + sl[i] * 128);
+                    uint4 av[8], sv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                // logical 16-byte chunk j sits at j ^ (r & 7) (128B swizzle)
+                        av[j] = arow[j ^ (r & 7)];
+                        sv[j] = srow[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        __half2* a2 = reinterpret_cast<__half2*>(&av[j]);
+                        const __half2* s2 = reinterpret_cast<const __half2*>(&sv[j]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) a2[e] = __hmul2(a2[e], s2[e]);
+                        arow[j ^ (r & 7)] = av[j];
+                    }
+                }
+                ptx::fence_proxy_async_smem();       // the rescaled tile must be visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(leader_ready0 + 8u * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp < 2 + EW) {
         // ===================== epilogue (both CTAs, own 128 rows) =====================
         const int q = warp & 3;
         const int slice = (warp - 2) >> 2;
@@ -821,14 +895,21 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     if (warp == 1) ptx::tmem_dealloc_cg2(tmem_base, TMEM_COLS);
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool ASCALE = false>
 static int launch_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tb_tail, int tail_bn,
                       const pb200_gemm_epilogue& ep, int M, int N, int K, cudaStream_t st) {
     constexpr int STAGES = BLOCK_N >= 256 ? 6 : 8;
-    constexpr int SMEM = STAGES * (GEMM_BLOCK_M * 128 + (BLOCK_N / 2) * 128) + 1024 + 256;
+    constexpr int SMEM = STAGES * (GEMM_BLOCK_M * 128 + (BLOCK_N / 2) * 128 + (ASCALE ? GEMM_ASCALE_BYTES : 0)) + 1024 + 512;
     static DeviceOnce attr_set;
     if (attr_set.first()) {
-        PB_CUDA(cudaFuncSetAttribute(gemm_f16_cg2_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        PB_CUDA(cudaFuncSetAttribute(gemm_f16_cg2_kernel<BLOCK_N, MODE, ASCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    }
+    CUtensorMap ts = ta;            // placeholder when unused
+    if (ASCALE) {
+        const int P = ep.rows_per_sample;
+        const int ns = P >= GEMM_BLOCK_M ? 1 : GEMM_BLOCK_M / P;
+        const int64_t samples = ((int64_t)M + P - 1) / P;
+        PB_TRY(make_tmap_f16_2d_box(&ts, ep.a_scale, samples, K, ep.a_scale_ld, GEMM_BLOCK_K, ns, 0));
     }
     const int n_big = ceil_div(M, 2 * GEMM_BLOCK_M) * ceil_div(N, BLOCK_N);
     const int max_pairs = sm_count() / 2;
@@ -839,7 +920,7 @@ static int launch_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(gemm_threads(BLOCK_N));
+    cfg.blockDim = dim3(gemm_threads(BLOCK_N) + (ASCALE ? 32 * GEMM_ASCALE_WARPS : 0));
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -852,7 +933,7 @@ static int launch_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 2 : 1;
-    PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_cg2_kernel<BLOCK_N, MODE>, ta, tb, *tb_tail, ep, M, N, K, n_main, tail_bn));
+    PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_cg2_kernel<BLOCK_N, MODE, ASCALE>, ta, tb, *tb_tail, ts, ep, M, N, K, n_main, tail_bn));
     PB_LAUNCH_CHECK();
     return 0;
 }
@@ -860,6 +941,11 @@ static int launch_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 template <int BLOCK_N>
 static int launch_cg2_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tb_tail, int tail_bn,
                            const pb200_gemm_epilogue& ep, int M, int N, int K, cudaStream_t st) {
+    if (ep.a_scale) {       // GlobalResponseNorm folded into the A operand: the two residual epilogues only
+        if (ep.mode == PB200_EPI_RESID_F32) return launch_cg2<BLOCK_N, PB200_EPI_RESID_F32, true>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
+        if (ep.mode == PB200_EPI_RESID_LN_F32) return launch_cg2<BLOCK_N, PB200_EPI_RESID_LN_F32, true>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
+        PB_CHECK(false, "gemm: a_scale is only built for the RESID epilogues (mode %d)", ep.mode);
+    }
     switch (ep.mode) {
         case PB200_EPI_F16: return launch_cg2<BLOCK_N, PB200_EPI_F16>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
         case PB200_EPI_F32: return launch_cg2<BLOCK_N, PB200_EPI_F32>(ta, tb, tb_tail, tail_bn, ep, M, N, K, st);
@@ -970,6 +1056,14 @@ static bool gemm_use_cg2(int64_t M) {
     return !off && M > GEMM_BLOCK_M && plan_sm_count() % 2 == 0;
 }
 
+bool gemm_can_scale_a(int64_t M, int64_t N, int64_t K, int rows_per_sample) {
+    static const bool off = getenv("PB200_NO_GRN_FOLD") != nullptr;      // A/B knob
+    const int P = rows_per_sample;
+    if (off || P <= 0 || !gemm_use_cg2(M) || K % GEMM_BLOCK_K != 0) return false;
+    if (!(P >= GEMM_BLOCK_M ? P % GEMM_BLOCK_M == 0 : (GEMM_BLOCK_M % P == 0 && GEMM_BLOCK_M / P <= 8))) return false;
+    return gemm_pick_block_n(M, N, K) >= 128;
+}
+
 int gemm_pick_block_n(int64_t M, int64_t N, int64_t K, bool allow_cg2) {
     // Cycle model per candidate BLOCK_N (measured anchors on B200, profiles/r01_cg2_gemm_notes.md):
     //   tensor   : waves x k-blocks x 4 MMAs x (BLOCK_N/2 cycles per 128-row MMA)
@@ -1038,6 +1132,9 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const
     if ((ep.mode == PB200_EPI_GELU_F16 && ep.sqsum) || ((ep.mode == PB200_EPI_RESID_F32 || ep.mode == PB200_EPI_RESID_LN_F32) && ep.film) ||
         ep.mode == PB200_EPI_NCHW_F32)
         PB_CHECK(ep.rows_per_sample > 0, "gemm: rows_per_sample required");
+    if (ep.a_scale)
+        PB_CHECK(gemm_can_scale_a(M, N, K, ep.rows_per_sample) && block_n >= 128 && ep.a_scale_ld % 8 == 0 && ((uintptr_t)ep.a_scale & 15) == 0,
+                 "gemm: a_scale needs the 2-SM kernel (M > 128), rows_per_sample dividing or divided by 128, K %% 64 == 0");
     static const char* kTags[8] = {"gemm_f16", "gemm_f32", "gemm_gelu_sqsum", "gemm_resid", "gemm_unpatch", "gemm_nchw",
                                    "gemm_resid", "gemm_f16"};
     ProfScope prof(ep.mode >= 0 && ep.mode < 8 ? kTags[ep.mode] : "gemm", 2.0 * (double)M * (double)N * (double)K, st);

@@ -53,6 +53,8 @@ int gemm_conv_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, 
 // BLOCK_N that minimises a tensor / L2-fabric cycle model of the launch (see gemm.cu); allow_cg2=false for the
 // conv (TMA-gather) variants, which run on the 1-SM kernel
 int gemm_pick_block_n(int64_t M, int64_t N, int64_t K = 0, bool allow_cg2 = true);
+// whether gemm_launch can take ep.a_scale for this problem (2-SM kernel, sample rows aligned with the 128-row tiles)
+bool gemm_can_scale_a(int64_t M, int64_t N, int64_t K, int rows_per_sample);
 
 // Narrow tiles for the leftover of the last wave (2-SM kernel, BLOCK_N 256): 0 = none, else 64 or 128; tb = tensor map of
 // W with box rows bn / 2.
