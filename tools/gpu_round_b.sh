@@ -4,6 +4,7 @@ TAG=${1:-r2b}
 O=gpurun_out
 mkdir -p $O
 if ls $O/*_attention_fallback.txt > /dev/null 2>&1; then export PB200_ATTN_LEGACY=1; echo "round B runs with PB200_ATTN_LEGACY=1"; fi
+if ls $O/*_dwslab_fallback.txt > /dev/null 2>&1; then export PB200_DWCONV_NOSLAB=1; echo "round B runs with PB200_DWCONV_NOSLAB=1"; fi
 if ls $O/*_grnfold_fallback.txt > /dev/null 2>&1; then export PB200_NO_GRN_FOLD=1; echo "round B runs with PB200_NO_GRN_FOLD=1"; fi
 B="python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-cuda-baseline"
 for sb in 0 32 16; do
@@ -17,6 +18,9 @@ except Exception as e:
     print("subbatch $sb: FAILED", e)
 PY
 done
+PB200_DWCONV_NOSLAB=1 timeout 300 $B > $O/${TAG}_bench_noslab.json 2> $O/${TAG}_bench_noslab.err
+python -c "
+import json; d=json.loads(open('$O/${TAG}_bench_noslab.json').read().strip().splitlines()[-1]); print('no dwconv slab:', round(d['value'],1), {k: v['ms'] for k, v in d['roofline']['families'].items() if 'dw' in k})"
 PB200_NO_GRN_FOLD=1 timeout 300 $B > $O/${TAG}_bench_nogrnfold.json 2> $O/${TAG}_bench_nogrnfold.err
 python -c "
 import json; d=json.loads(open('$O/${TAG}_bench_nogrnfold.json').read().strip().splitlines()[-1]); print('no GRN fold:', round(d['value'],1), {k: v['ms'] for k, v in d['roofline']['families'].items()})"
