@@ -60,7 +60,20 @@ def _run(B, P, S, H, hd, self_attn, varlen, weighted, seed=0):
     torch.cuda.synchronize()
     want = _reference(qkv, ckv, kv_len, B, P, S, E, H, self_attn, aw)
     d = out.float() - want
-    return float(d.abs().max()), float(d.pow(2).mean().sqrt()), out
+    mx = float(d.abs().nan_to_num(1e9).max())
+    if not (mx < 4e-3):          # layout diagnostics for a wrong kernel: error per (16-row block, 16-column block) of sample 0 / head 0,
+        lines = [f"case B={B} P={P} S={S} H={H} hd={hd} self={self_attn} varlen={varlen} weighted={weighted}: max {mx:.3e}"]      # and per (sample, head)
+        e = d.abs().nan_to_num(9.0).view(B, P, H, hd)
+        lines.append("per (sample, head) max: " + " ".join(f"{float(e[b, :, h].max()):.1e}" for b in range(min(B, 4)) for h in range(min(H, 4))))
+        blk = e[0, :, 0]
+        for r0 in range(0, P, 16):
+            lines.append(f"rows {r0:3d}+16: " + " ".join(f"{float(blk[r0:r0 + 16, c0:c0 + 16].max()):.1e}" for c0 in range(0, hd, 16)))
+        lines.append("nan count: %d" % int(torch.isnan(out.float()).sum()))
+        lines.append("got[0,:4,:6]  " + str(out.float().view(B, P, H, hd)[0, :4, 0, :6].tolist()))
+        lines.append("want[0,:4,:6] " + str(want.view(B, P, H, hd)[0, :4, 0, :6].tolist()))
+        _log({"debug": lines})
+        print("\n".join(lines))
+    return mx, float(d.nan_to_num(1e9).pow(2).mean().sqrt()), out
 
 
 # (B, P, S, heads, head_dim, self_attn, varlen, weighted)
