@@ -262,6 +262,7 @@ class TimestepBlock(nn.Module):
 # A/B knob: run guided steps in groups of this many (cond, uncond) pairs so that a block's activations stay L2-resident
 # (0 = whole batch at once).  See Paella._features_chunked.
 _SUBBATCH_PAIRS = int(os.environ.get("PB200_SUBBATCH", "0") or 0)
+_SUBBATCH_STREAMS = int(os.environ.get("PB200_STREAMS", "1") or 1)
 
 
 class ConditioningCache:
@@ -346,6 +347,7 @@ class Paella(nn.Module):
         self._packed_key = None
         self._workspace = None
         self._cond_single = None
+        self._side_streams = None
 
     # -------------------------------------------------------------- initialisation (ref/src/modules.py:189-210)
     def _reference_init(self, blocks, num_labels):
@@ -485,9 +487,16 @@ class Paella(nn.Module):
         return m
 
     def _ws(self, nbytes: int) -> torch.Tensor:
-        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != self._device():
-            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self._device())
-        return self._workspace
+        """Scratch for the launches of ONE stream (the library bump-allocates it identically on every call): one buffer per
+        CUDA stream the model is driven from, so concurrent sub-batches (Paella._features_chunked) never share scratch."""
+        if not isinstance(self._workspace, dict):
+            self._workspace = {}
+        key = torch.cuda.current_stream(self._device()).cuda_stream
+        ws = self._workspace.get(key)
+        if ws is None or ws.numel() < nbytes or ws.device != self._device():
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self._device())
+            self._workspace[key] = ws
+        return ws
 
     # -------------------------------------------------------------- conditioning
     def prepare_conditioning(self, groups: Sequence[Dict[str, torch.Tensor]], latent_hw=(32, 32),
@@ -638,7 +647,13 @@ class Paella(nn.Module):
         n_tok = H * W
         full = torch.empty(2 * B * n_tok, self._cfg["c_out"], dtype=torch.float32, device=dev)
         maps = cond.__dict__.setdefault("_chunk_maps", {})
-        for lo in range(0, B, chunk):
+        main = torch.cuda.current_stream(dev)
+        side = []
+        if _SUBBATCH_STREAMS > 1:       # groups are independent: run them on their own streams so that one group's launch gaps,
+            if getattr(self, "_side_streams", None) is None or len(self._side_streams) != _SUBBATCH_STREAMS:      # tails and memory-
+                self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(_SUBBATCH_STREAMS)]           # bound kernels
+            side = self._side_streams                                                                             # overlap the other's
+        for i, lo in enumerate(range(0, B, chunk)):
             hi = min(B, lo + chunk)
             key = (lo, hi, B)
             if key not in maps:
@@ -646,10 +661,18 @@ class Paella(nn.Module):
                 maps[key] = torch.cat([base[lo:hi], base[B + lo:B + hi]]).contiguous()
             sub = ConditioningCache(cond.cache, 2 * (hi - lo), cond.s_max, cond.slots, maps[key])
             aw_b = max(0, min(attn_weights_batch, hi) - lo) if attn_weights is not None else 0
-            f = self.features(x[lo:hi], r[lo:hi], sub, attn_weights, aw_b, cfg_pairs=True)
-            n = (hi - lo) * n_tok
-            full[lo * n_tok:hi * n_tok] = f[:n]
-            full[(B + lo) * n_tok:(B + hi) * n_tok] = f[n:]
+            st = side[i % len(side)] if side else main
+            if side:
+                st.wait_stream(main)
+            with torch.cuda.stream(st):
+                f = self.features(x[lo:hi], r[lo:hi], sub, attn_weights, aw_b, cfg_pairs=True)
+                n = (hi - lo) * n_tok
+                full[lo * n_tok:hi * n_tok] = f[:n]
+                full[(B + lo) * n_tok:(B + hi) * n_tok] = f[n:]
+                if side:
+                    f.record_stream(st)
+        for st in side:
+            main.wait_stream(st)
         return full
 
     def logits_from_features(self, feats: torch.Tensor, batch: int, h: int, w: int) -> torch.Tensor:

@@ -18,6 +18,15 @@ except Exception as e:
     print("subbatch $sb: FAILED", e)
 PY
 done
+for cfg in "32 2" "16 2" "16 4"; do
+  set -- $cfg
+  PB200_SUBBATCH=$1 PB200_STREAMS=$2 timeout 300 $B > $O/${TAG}_bench_sub$1_str$2.json 2> $O/${TAG}_bench_sub$1_str$2.err
+  python -c "
+import json
+try:
+    d=json.loads(open('$O/${TAG}_bench_sub$1_str$2.json').read().strip().splitlines()[-1]); print('subbatch $1 streams $2:', round(d['value'],1), 'img/s', round(d['ms_per_step'],1), 'ms')
+except Exception as e: print('subbatch $1 streams $2 FAILED', e)"
+done
 PB200_DWCONV_NOSLAB=1 timeout 300 $B > $O/${TAG}_bench_noslab.json 2> $O/${TAG}_bench_noslab.err
 python -c "
 import json; d=json.loads(open('$O/${TAG}_bench_noslab.json').read().strip().splitlines()[-1]); print('no dwconv slab:', round(d['value'],1), {k: v['ms'] for k, v in d['roofline']['families'].items() if 'dw' in k})"
