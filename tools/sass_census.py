@@ -13,6 +13,7 @@ for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
         fn = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        fn = fn.replace("(anonymous namespace)::", "")
         fn = re.sub(r"\(.*", "", fn).replace("void ", "").replace("pb::", "")
         fn = fn.replace("(int)", "").replace("(bool)", "")
         counts[fn] = collections.Counter()
