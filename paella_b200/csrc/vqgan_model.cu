@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) vq_out_block_kernel(const float* __restri
         if (MODE == 2) {
             uint8_t* img = reinterpret_cast<uint8_t*>(img_out);
             img[(((int64_t)b * (2 * h2) + 2 * y + (d >> 1)) * (2 * w2) + 2 * xx + (d & 1)) * 3 + c] =
-                (uint8_t)fminf(v * 255.0f + 0.5f, 255.0f);
+                (uint8_t)fminf(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f), 255.0f);      // mul then add, two roundings like the torch ops (no FMA)
         } else {
             float* img = reinterpret_cast<float*>(img_out);
             img[(((int64_t)b * 3 + c) * (2 * h2) + 2 * y + (d >> 1)) * (2 * w2) + 2 * xx + (d & 1)] = v;
