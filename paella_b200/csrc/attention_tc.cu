@@ -21,10 +21,6 @@
 #include "attention.cuh"
 #include "gemm.cuh"
 
-#include <map>
-#include <mutex>
-#include <tuple>
-
 namespace pb {
 namespace {
 
@@ -351,31 +347,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
     if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-struct TmapKey {
-    const void* ptr;
-    int64_t rows, cols;
-    int box_cols, box_rows;
-    bool operator<(const TmapKey& o) const {
-        return std::tie(ptr, rows, cols, box_cols, box_rows) < std::tie(o.ptr, o.rows, o.cols, o.box_cols, o.box_rows);
-    }
-};
-
-// tensor maps are pure functions of (pointer, shape, box): the model's workspace is bump-allocated identically every call, so
-// a small cache removes the driver call from all but the first launches
 int cached_tmap(const void* ptr, int64_t rows, int64_t cols, int box_cols, int box_rows, CUtensorMap* out) {
-    static std::map<TmapKey, CUtensorMap> cache;
-    static std::mutex mu;
-    const TmapKey key{ptr, rows, cols, box_cols, box_rows};
-    std::lock_guard<std::mutex> lk(mu);
-    auto it = cache.find(key);
-    if (it == cache.end()) {
-        if (cache.size() > 4096) cache.clear();
-        CUtensorMap tm;
-        PB_TRY(make_tmap_f16_2d_box(&tm, ptr, rows, cols, cols, box_cols, box_rows, box_cols == 64 ? 128 : 32));
-        it = cache.emplace(key, tm).first;
-    }
-    *out = it->second;
-    return 0;
+    return cached_tmap_f16_2d(ptr, rows, cols, cols, box_cols, box_rows, box_cols == 64 ? 128 : 32, out);
 }
 
 }  // namespace

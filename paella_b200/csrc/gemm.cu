@@ -22,7 +22,9 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <unordered_map>
 
 namespace pb {
@@ -85,6 +87,26 @@ int make_tmap_f16_2d_box(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t
     return 0;
 }
 
+// Tensor maps are pure functions of (pointer, shape, box): the executors' workspaces are bump-allocated identically every call
+// and the weights never move, so a process-wide cache removes the driver call from all but the first launches.
+int cached_tmap_f16_2d(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int swizzle_bytes,
+                       CUtensorMap* out) {
+    using Key = std::tuple<const void*, int64_t, int64_t, int64_t, int, int, int>;
+    static std::map<Key, CUtensorMap> cache;
+    static std::mutex mu;
+    const Key key{ptr, rows, cols, ld, box_cols, box_rows, swizzle_bytes};
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        if (cache.size() > 8192) cache.clear();
+        CUtensorMap tm;
+        PB_TRY(make_tmap_f16_2d_box(&tm, ptr, rows, cols, ld, box_cols, box_rows, swizzle_bytes));
+        it = cache.emplace(key, tm).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
 // rank-N fp16 tensor map (dims/strides innermost first, strides in bytes for dims 1..rank-1), 128-byte swizzle
 int make_tmap_f16_nd(CUtensorMap* tm, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes,
                      const int* box) {
@@ -138,24 +160,6 @@ struct EpiPre<PB200_EPI_RESID_LN_F32> {
 //         (a store instruction then writes 4 full 128-byte lines);
 //   fp16: 4x4 transpose of 8-half items in 4-lane groups -> lane (a,b) item i = row 4a+i, columns 8b..8b+7
 //         (8 rows x 64 contiguous bytes per instruction).
-__device__ __forceinline__ void transpose8x8_f4(float (&v)[32], int lane) {
-#pragma unroll
-    for (int s = 4; s > 0; s >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int g0 = 0; g0 < 8; ++g0) {
-            if (g0 & s) continue;
-            const int g1 = g0 | s;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float send = up ? v[g0 * 4 + e] : v[g1 * 4 + e];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, s);
-                if (up) v[g0 * 4 + e] = recv;
-                else v[g1 * 4 + e] = recv;
-            }
-        }
-    }
-}
 __device__ __forceinline__ void transpose4x4_u4(uint32_t (&pk)[16], int lane) {
 #pragma unroll
     for (int s = 2; s > 0; s >>= 1) {

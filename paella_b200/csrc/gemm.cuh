@@ -31,6 +31,10 @@ int make_tmap_f16_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t col
 int make_tmap_f16_2d_box(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
                          int swizzle_bytes);
 
+// ... through a process-wide cache keyed by (pointer, shape, box, swizzle)
+int cached_tmap_f16_2d(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int swizzle_bytes,
+                       CUtensorMap* out);
+
 int make_tmap_f16_nd(CUtensorMap* tm, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes,
                      const int* box);
 
@@ -70,5 +74,26 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const
 // convenience: builds both tensor maps and launches
 int gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int64_t N, int64_t K,
              const pb200_gemm_epilogue& ep, cudaStream_t st);
+
+// In-warp 8x8 transpose of float4 items (xor-butterfly shuffles): tcgen05.ld hands lane l row l of a 32-column chunk; afterwards
+// item i of lane (a, b) = row 8a + i, columns 4b..4b+3, so one store instruction writes four full 128-byte lines.
+__device__ __forceinline__ void transpose8x8_f4(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 4; s > 0; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int g0 = 0; g0 < 8; ++g0) {
+            if (g0 & s) continue;
+            const int g1 = g0 | s;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float send = up ? v[g0 * 4 + e] : v[g1 * 4 + e];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+                if (up) v[g0 * 4 + e] = recv;
+                else v[g1 * 4 + e] = recv;
+            }
+        }
+    }
+}
 
 }  // namespace pb
