@@ -75,6 +75,11 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int block_n, const
 int gemm_f16(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int64_t N, int64_t K,
              const pb200_gemm_epilogue& ep, cudaStream_t st);
 
+// Fused MLP of the codec ResBlock (vq_mlp.cu): x[M, C] += alpha * (GELU(a16 W1^T + b1) W2^T + b2), hidden kept on chip.
+// 0 = launched, 1 = error, -1 = shape not handled (C not in {384, 192} or M < 256): the caller runs the two GEMMs instead.
+int launch_vq_mlp_fused(const __half* a16, int64_t M, int C, const __half* w1, const float* b1, const __half* w2, const float* b2,
+                        float* x, float alpha, cudaStream_t st);
+
 // In-warp 8x8 transpose of float4 items (xor-butterfly shuffles): tcgen05.ld hands lane l row l of a 32-column chunk; afterwards
 // item i of lane (a, b) = row 8a + i, columns 4b..4b+3, so one store instruction writes four full 128-byte lines.
 __device__ __forceinline__ void transpose8x8_f4(float (&v)[32], int lane) {

@@ -5,6 +5,7 @@ O=gpurun_out
 mkdir -p $O
 if ls $O/*_attention_fallback.txt > /dev/null 2>&1; then export PB200_ATTN_LEGACY=1; echo "round B runs with PB200_ATTN_LEGACY=1"; fi
 if ls $O/*_dwslab_fallback.txt > /dev/null 2>&1; then export PB200_DWCONV_NOSLAB=1; echo "round B runs with PB200_DWCONV_NOSLAB=1"; fi
+if ls $O/*_vqmlp_fallback.txt > /dev/null 2>&1; then export PB200_VQ_MLP_UNFUSED=1; echo "round B runs with PB200_VQ_MLP_UNFUSED=1"; fi
 if ls $O/*_grnfold_fallback.txt > /dev/null 2>&1; then export PB200_NO_GRN_FOLD=1; echo "round B runs with PB200_NO_GRN_FOLD=1"; fi
 B="python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-cuda-baseline"
 for sb in 0 32 16; do
@@ -44,6 +45,12 @@ try:
     d=json.loads(open('$O/${TAG}_vqgan_sub${vs}.json').read().strip().splitlines()[-1]); print('vqgan sub $vs:', round(d['value'],1), 'img/s', {k: round(v['ms'],2) for k, v in d['roofline']['families'].items()})
 except Exception as e: print('vqgan sub $vs FAILED', e)"
 done
+PB200_VQ_MLP_UNFUSED=1 timeout 300 python bench.py --workload vqgan --batch 64 --steps 3 --warmup 3 --no-cpu-baseline --no-cuda-baseline > $O/${TAG}_vqgan_unfused.json 2> $O/${TAG}_vqgan_unfused.err
+python -c "
+import json
+try:
+    d=json.loads(open('$O/${TAG}_vqgan_unfused.json').read().strip().splitlines()[-1]); print('vqgan unfused MLP:', round(d['value'],1), 'img/s', {k: round(v['ms'],2) for k, v in d['roofline']['families'].items()})
+except Exception as e: print('vqgan unfused FAILED', e)"
 timeout 600 python bench.py --workload vqgan --steps 3 --warmup 3 --no-cpu-baseline > $O/${TAG}_vqgan_full.json 2> $O/${TAG}_vqgan_full.err
 tail -c 1200 $O/${TAG}_vqgan_full.json
 timeout 600 python bench.py --workload sample64 --steps 3 --warmup 3 --no-cpu-baseline > $O/${TAG}_sample64.json 2> $O/${TAG}_sample64.err
