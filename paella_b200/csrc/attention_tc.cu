@@ -15,9 +15,13 @@
 // tcgen05.mma instructions (same accumulator along K for Q/K, adjacent accumulator columns along N for V).
 // An M=64 accumulator occupies 16 lanes of each of the four TMEM sub-partitions (row r -> lane 32*(r/16) + r%16; CUTLASS
 // cute/atom/mma_traits_sm100.hpp tmem_frg, M_MMA == 64), so each softmax / epilogue warp owns 16 query rows.
-// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer + TMEM allocator, 4-7 softmax, 8-11 epilogue (2-3 idle: a warp may
+// Warp roles (512 threads): 0 TMA producer, 1 MMA issuer + TMEM allocator, 2-3 loaders of the 16-wide operand tails, 4-7 and
+// 8-11 two softmax groups taking alternate query tiles (one group when S / P are single-buffered), 12-15 epilogue (a warp may
 // only touch the TMEM lanes of sub-partition warp_id % 4).  Pipelines (mbarriers): Q ring (2), K/V ring (2, or 1 when the tile
 // is large), S accumulators (2 if 2*keys + 80 <= 512 TMEM columns), P buffers (2 if shared memory allows), one O accumulator.
+// The 16-wide tails (20 % of the bytes) would be half of all TMA row requests as 32-byte boxes -- TMA issues one request per
+// box row, and round 2's first version spent ~9 600 cycles per (sample, head) unit on 1 800 of them -- so warps 2-3 bring the
+// tails in with 16-byte cp.async into the same 32B-swizzle layout and arrive on the same mbarrier (cp.async.mbarrier.arrive).
 #include "attention.cuh"
 #include "gemm.cuh"
 
@@ -26,7 +30,8 @@ namespace {
 
 constexpr int TC_HD = 80;
 constexpr int TC_QT = 64;
-constexpr int TC_THREADS = 384;
+constexpr int TC_THREADS = 512;
+constexpr int TC_TAIL_THREADS = 64;
 constexpr int TC_O_COLS = 80;
 
 struct TcParams {
@@ -36,6 +41,10 @@ struct TcParams {
     int sbox;          // rows of one conditioning TMA box
     int n1;            // S columns = MMA1 N = self_rows + sbox (multiple of 16)
     int nkv, nsb, npb; // ring depths: K/V stages, S accumulators, P buffers
+    int tails_cp;      // 16-wide tails by cp.async (warps 2-3) instead of 32-byte TMA boxes
+    const __half* qkv; // raw pointers for the cp.async tail loads
+    const __half* ckv;
+    int c_rows;        // rows of the conditioning tensor (slots * S_max)
     const int* kv_len;
     const int* kv_slot;
     float scale_log2;
@@ -80,9 +89,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
     }
     if (warp == 1) {
         if (lane == 0) {
+            const uint32_t ld_cnt = 1u + (p.tails_cp ? TC_TAIL_THREADS : 0u);      // TMA thread (+ the tail loaders' cp.async arrivals)
             for (int i = 0; i < 2; ++i) {
-                ptx::mbar_init(bar(BAR_QF + i), 1);  ptx::mbar_init(bar(BAR_QE + i), 1);
-                ptx::mbar_init(bar(BAR_KVF + i), 1); ptx::mbar_init(bar(BAR_KVE + i), 1);
+                ptx::mbar_init(bar(BAR_QF + i), ld_cnt);  ptx::mbar_init(bar(BAR_QE + i), 1);
+                ptx::mbar_init(bar(BAR_KVF + i), ld_cnt); ptx::mbar_init(bar(BAR_KVE + i), 1);
                 ptx::mbar_init(bar(BAR_SF + i), 1);  ptx::mbar_init(bar(BAR_SE + i), 4);
                 ptx::mbar_init(bar(BAR_PF + i), 4);  ptx::mbar_init(bar(BAR_PE + i), 1);
             }
@@ -115,27 +125,82 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 const int st = uc % p.nkv;
                 ptx::mbar_wait(bar(BAR_KVE + st), (((uint32_t)(uc / p.nkv)) & 1u) ^ 1u);
                 const uint32_t fb = bar(BAR_KVF + st);
-                ptx::mbar_arrive_expect_tx(fb, 2u * (uint32_t)(p.self_rows + p.sbox) * 160u);
+                ptx::mbar_arrive_expect_tx(fb, 2u * (uint32_t)(p.self_rows + p.sbox) * (p.tails_cp ? 128u : 160u));
                 const uint32_t k64 = kv_stage(st), v64 = k64 + p.k64_bytes, k16 = v64 + p.k64_bytes, v16 = k16 + p.k16_bytes;
                 const int hc = h * TC_HD;
                 if (p.self_rows) {
                     const int row0 = b * p.P;
                     ptx::tma_load_2d(&tm_s64, fb, k64, p.E + hc, row0);
                     ptx::tma_load_2d(&tm_s64, fb, v64, 2 * p.E + hc, row0);
-                    ptx::tma_load_2d(&tm_s16, fb, k16, p.E + hc + 64, row0);
-                    ptx::tma_load_2d(&tm_s16, fb, v16, 2 * p.E + hc + 64, row0);
+                    if (!p.tails_cp) {
+                        ptx::tma_load_2d(&tm_s16, fb, k16, p.E + hc + 64, row0);
+                        ptx::tma_load_2d(&tm_s16, fb, v16, 2 * p.E + hc + 64, row0);
+                    }
                 }
                 const int crow = slot * p.S_max;
                 ptx::tma_load_2d(&tm_c64, fb, k64 + (uint32_t)p.self_rows * 128u, hc, crow);
                 ptx::tma_load_2d(&tm_c64, fb, v64 + (uint32_t)p.self_rows * 128u, p.E + hc, crow);
-                ptx::tma_load_2d(&tm_c16, fb, k16 + (uint32_t)p.self_rows * 32u, hc + 64, crow);
-                ptx::tma_load_2d(&tm_c16, fb, v16 + (uint32_t)p.self_rows * 32u, p.E + hc + 64, crow);
+                if (!p.tails_cp) {
+                    ptx::tma_load_2d(&tm_c16, fb, k16 + (uint32_t)p.self_rows * 32u, hc + 64, crow);
+                    ptx::tma_load_2d(&tm_c16, fb, v16 + (uint32_t)p.self_rows * 32u, p.E + hc + 64, crow);
+                }
                 for (int qt = 0; qt < p.n_qt; ++qt, ++it) {
                     const int qs = it & 1;
                     ptx::mbar_wait(bar(BAR_QE + qs), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
-                    ptx::mbar_arrive_expect_tx(bar(BAR_QF + qs), Q_BYTES);
+                    ptx::mbar_arrive_expect_tx(bar(BAR_QF + qs), p.tails_cp ? TC_QT * 128u : Q_BYTES);
                     ptx::tma_load_2d(&tm_q64, bar(BAR_QF + qs), q64(qs), hc, b * p.P + qt * TC_QT);
-                    ptx::tma_load_2d(&tm_q16, bar(BAR_QF + qs), q16(qs), hc + 64, b * p.P + qt * TC_QT);
+                    if (!p.tails_cp) ptx::tma_load_2d(&tm_q16, bar(BAR_QF + qs), q16(qs), hc + 64, b * p.P + qt * TC_QT);
+                }
+            }
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ===================== tail loaders: the 16-wide K / V / Q slices by cp.async, 32B-swizzle layout =====================
+        if (p.tails_cp) {
+            const int t = (warp - 2) * 32 + lane;
+            // tile row r, 16-byte chunk c (0/1) of a [rows x 32 B] SWIZZLE_32B tile lives at r*32 + ((c ^ ((r >> 2) & 1)) << 4)
+            auto dst = [](uint32_t tile, int r, int c) { return tile + (uint32_t)(r * 32 + ((c ^ ((r >> 2) & 1)) << 4)); };
+            const int64_t ldq = 3 * (int64_t)p.E, ldc = 2 * (int64_t)p.E;
+            const int q_rows = p.B * p.P;
+            int it = 0, uc = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
+                const int b = u / p.nhead, h = u - b * p.nhead;
+                const int slot = p.kv_slot ? p.kv_slot[b] : b;
+                const int st = uc % p.nkv;
+                ptx::mbar_wait(bar(BAR_KVE + st), (((uint32_t)(uc / p.nkv)) & 1u) ^ 1u);
+                const uint32_t k16 = kv_stage(st) + 2 * p.k64_bytes, v16 = k16 + p.k16_bytes;
+                const int col = h * TC_HD + 64;
+                const int n_rows = p.self_rows + p.sbox;
+                for (int i = t; i < n_rows * 2; i += TC_TAIL_THREADS) {
+                    const int r = i >> 1, c = i & 1;
+                    const __half* ks;
+                    bool ok = true;
+                    if (r < p.self_rows) {
+                        ks = p.qkv + ((int64_t)b * p.P + r) * ldq + p.E + col + c * 8;
+                    } else {
+                        const int64_t cr = (int64_t)slot * p.S_max + (r - p.self_rows);
+                        ok = cr < p.c_rows;
+                        ks = p.ckv + (ok ? cr : 0) * ldc + col + c * 8;
+                    }
+                    ptx::cp_async16(dst(k16, r, c), ks, ok);
+                    ptx::cp_async16(dst(v16, r, c), ks + p.E, ok);          // v sits E columns after k in both tensors
+                }
+                // cp.async writes through the generic proxy: wait for this thread's copies, make them visible to the tensor core's
+                // async proxy, then arrive (the loaders have nothing else to do; the next unit's stage is a different buffer)
+                asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                ptx::fence_proxy_async_smem();
+                ptx::mbar_arrive(bar(BAR_KVF + st));
+                for (int qt = 0; qt < p.n_qt; ++qt, ++it) {
+                    const int qs = it & 1;
+                    ptx::mbar_wait(bar(BAR_QE + qs), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+                    for (int i = t; i < TC_QT * 2; i += TC_TAIL_THREADS) {
+                        const int r = i >> 1, c = i & 1;
+                        const int64_t gr = (int64_t)b * p.P + qt * TC_QT + r;
+                        const bool ok = gr < q_rows;
+                        ptx::cp_async16(dst(q16(qs), r, c), p.qkv + (ok ? gr : 0) * ldq + col + c * 8, ok);
+                    }
+                    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                    ptx::fence_proxy_async_smem();
+                    ptx::mbar_arrive(bar(BAR_QF + qs));
                 }
             }
         }
@@ -216,12 +281,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
             if (valid(n) && !ahead) issue_s(n);
             c = n;
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 12) {
         // ===================== softmax: S (TMEM) -> P (shared, fp16, K-major 128B swizzle) =====================
+        // two groups of four warps take alternate query tiles when S and P are double-buffered (each tile is private to one
+        // group: no cross-warp reduction, the barriers still see four arrivals per tile)
+        const int group = (warp - 4) >> 2;
+        const int n_groups = (p.nsb == 2 && p.npb == 2) ? 2 : 1;
         const int wq = warp & 3;
         const int row = wq * 16 + lane;                 // query row of this thread inside the tile (lanes 16..31 carry none)
         const bool lane_ok = lane < 16;
         int it = 0;
+        if (group < n_groups)
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int b = u / p.nhead;
             const int slot = p.kv_slot ? p.kv_slot[b] : b;
@@ -230,6 +300,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
             const bool weighted = p.attn_w != nullptr && b < p.w_batch && p.n_w > 0;
             const int w_start = nk - p.n_w;
             for (int qt = 0; qt < p.n_qt; ++qt, ++it) {
+                if (it % n_groups != group) continue;
                 const int sb = it % p.nsb, pb = it % p.npb;
                 const bool rows_here = qt * TC_QT + wq * 16 < p.P;         // warp-uniform: any real query in this warp's 16 rows
                 ptx::mbar_wait(bar(BAR_SF + sb), ((uint32_t)(it / p.nsb)) & 1u);
@@ -237,15 +308,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 const uint32_t ts = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(sb * p.n1);
                 float m = -INFINITY;
                 if (rows_here) {
-                    for (int c0 = 0; c0 < nk; c0 += 32) {
-                        float v[32];
-                        ptx::tmem_ld_32x32(ts + (uint32_t)c0, v);
-                        if (c0 + 32 <= nk) {
+                    for (int c0 = 0; c0 < nk; c0 += 64) {
+                        float v[64];
+                        ptx::tmem_ld_32x64(ts + (uint32_t)c0, v);
+                        if (c0 + 64 <= nk) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
+                            for (int j = 0; j < 64; ++j) m = fmaxf(m, v[j]);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) m = (c0 + j < nk) ? fmaxf(m, v[j]) : m;
+                            for (int j = 0; j < 64; ++j) m = (c0 + j < nk) ? fmaxf(m, v[j]) : m;
                         }
                     }
                 }
@@ -254,31 +325,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 if (rows_here) {
                     const float msc = m * p.scale_log2;
                     uint8_t* prow = smem_gen + p.off_p + (size_t)pb * p.p_bytes + (size_t)row * 128;
-                    for (int c0 = 0; c0 < nk16; c0 += 32) {
-                        float v[32];
-                        ptx::tmem_ld_32x32(ts + (uint32_t)c0, v);
+                    for (int c0 = 0; c0 < nk16; c0 += 64) {      // one 64-key atom of the P tile per iteration
+                        float v[64];
+                        ptx::tmem_ld_32x64(ts + (uint32_t)c0, v);
+                        const bool full = c0 + 64 <= nk;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float e = exp2f(fmaf(v[j], p.scale_log2, -msc));
-                            v[j] = (c0 + j < nk) ? e : 0.f;
+                        for (int j = 0; j < 64; ++j) {
+                            const float e = ptx::ex2_approx(fmaf(v[j], p.scale_log2, -msc));
+                            v[j] = (full || c0 + j < nk) ? e : 0.f;
                             l += v[j];
                         }
                         if (weighted) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
+                            for (int j = 0; j < 64; ++j) {
                                 const int kj = c0 + j;
                                 if (kj >= w_start && kj < nk) v[j] *= p.attn_w[kj - w_start];
                             }
                         }
                         if (lane_ok) {
                             uint8_t* atom = prow + (size_t)(c0 >> 6) * 8192;
-                            const int ck0 = (c0 & 63) >> 3;      // first 16-byte chunk (8 keys) of this 32-key group inside the atom
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
+                            for (int g = 0; g < 8; ++g) {
                                 uint4 pk;
                                 pk.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
                                 pk.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
-                                *reinterpret_cast<uint4*>(atom + (((ck0 + g) ^ (row & 7)) << 4)) = pk;
+                                *reinterpret_cast<uint4*>(atom + ((g ^ (row & 7)) << 4)) = pk;
                             }
                         }
                     }
@@ -293,7 +364,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 12) {
         // ===================== epilogue: O (TMEM) / rowsum -> fp16 -> global =====================
         const int wq = warp & 3;
         const int row = wq * 16 + lane;
@@ -369,6 +440,10 @@ int launch_attention_tc(const AttnParams& a, cudaStream_t st) {
     p.n1 = (p.self_rows + a.S_max + 15) & ~15;
     p.sbox = p.n1 - p.self_rows;
     if (p.sbox > 256 || p.n1 + TC_O_COLS > 512 || (p.n1 > 256 && p.n1 - 256 < 16)) return -1;
+    static const bool tails_tma = getenv("PB200_ATTN_TAILS_TMA") != nullptr;      // A/B knob: 32-byte TMA boxes for the tails
+    p.tails_cp = tails_tma ? 0 : 1;
+    p.qkv = a.qkv; p.ckv = a.ckv;
+    p.c_rows = (a.n_slots > 0 ? a.n_slots : a.B) * a.S_max;
     p.kv_len = a.kv_len; p.kv_slot = a.kv_slot; p.scale_log2 = a.scale_log2;
     p.attn_w = a.attn_w; p.n_w = a.attn_w ? a.n_w : 0; p.w_batch = a.w_batch; p.out = a.out;
     p.k64_bytes = (uint32_t)p.n1 * 128u;

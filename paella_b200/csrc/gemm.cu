@@ -643,10 +643,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 // ASCALE (GlobalResponseNorm folded into the A operand, ref/src/modules.py:37-40 + :53): the A tile is multiplied in shared
 // memory, between TMA and MMA, by a per-(sample, k) fp16 factor  s[b, k] = 1 + gamma[k] * Nx[b, k]  -- GEMM2 of a ResBlock then
 // computes (h * s) W2^T + (W2 beta + b2) = GRN(h) W2^T + b2 without the separate read-modify-write pass over the 4c-wide hidden.
-// Two extra warps per CTA (64 threads, two rows each) transform every stage: the A tile and the [samples x 64] slice of s land on
+// Four extra warps per CTA (one thread per row) transform every stage: the A tile and the [samples x 64] slice of s land on
 // a CTA-local barrier (afull), the transform warps rescale the swizzled rows in place, fence the generic->async proxy and arrive
 // on the leader's ready[s]; the MMA thread waits for full[s] (both W halves) and ready[s] (both CTAs' A tiles transformed).
-constexpr int GEMM_ASCALE_WARPS = 2;
+constexpr int GEMM_ASCALE_WARPS = 4;         // one thread per row of the 128-row A tile
 constexpr int GEMM_ASCALE_BYTES = 1024;        // up to 8 samples x 64 factors per 128-row tile and k-block
 template <int BLOCK_N, int MODE, bool ASCALE>
 __global__ void __launch_bounds__(gemm_threads(BLOCK_N) + (ASCALE ? 32 * GEMM_ASCALE_WARPS : 0), 1)
@@ -811,9 +811,10 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
     } else if (ASCALE && warp >= 2 + EW) {
         // ===================== A-operand transform (both CTAs, own 128 rows) =====================
-        const int t = (warp - 2 - EW) * 32 + lane;          // 0..63: rows t and t + 64 of the tile
+        const int r = (warp - 2 - EW) * 32 + lane;          // this thread's row of the 128-row tile
         const int P = ep.rows_per_sample;
         const int ns = P >= GEMM_BLOCK_M ? 1 : GEMM_BLOCK_M / P;
+        const int sl = P >= GEMM_BLOCK_M ? 0 : min(r / P, ns - 1);          // factor row = sample of this row inside the tile
         const uint32_t leader_ready0 = ptx::mapa(ready_bar(0), 0);
         uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
         int stage = 0;
@@ -821,35 +822,24 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         for (int unit = unit0; unit < n_units; unit += unit_step) {
             const Unit un = decode(unit);
             if (un.width == 0) continue;
-            int sl[2];                                           // factor row (sample inside the tile) of this thread's two rows
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int r = t + 64 * i;
-                sl[i] = P >= GEMM_BLOCK_M ? 0 : min(r / P, ns - 1);
-            }
             for (int kb = 0; kb < n_kb; ++kb) {
                 ptx::mbar_wait(afull_bar(stage), phase);
                 uint8_t* sa = smem_gen + stage * STAGE_BYTES;
-                const uint8_t* sc = sa + A_BYTES + BH_BYTES;
+                uint4* arow = reinterpret_cast<uint4*>(sa + r * 128);
+                const uint4* srow = reinterpret_cast<const uint4*>(sa + A_BYTES + BH_BYTES + sl * 128);
+                uint4 av[8], sv[8];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int r = t + 64 * i;
-                    uint4* arow = reinterpret_cast<uint4*>(sa + r * 128);
-                    const uint4* srow = reinterpret_cast<const uint4*>(sc + sl[i] * 128);
-                    uint4 av[8], sv[8];
+                for (int j = 0; j < 8; ++j) {                // logical 16-byte chunk j sits at j ^ (r & 7) (128B swizzle)
+                    av[j] = arow[j ^ (r & 7)];
+                    sv[j] = srow[j];
+                }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {                // logical 16-byte chunk j sits at j ^ (r & 7) (128B swizzle)
-                        av[j] = arow[j ^ (r & 7)];
-                        sv[j] = srow[j];
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    __half2* a2 = reinterpret_cast<__half2*>(&av[j]);
+                    const __half2* s2 = reinterpret_cast<const __half2*>(&sv[j]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        __half2* a2 = reinterpret_cast<__half2*>(&av[j]);
-                        const __half2* s2 = reinterpret_cast<const __half2*>(&sv[j]);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) a2[e] = __hmul2(a2[e], s2[e]);
-                        arow[j ^ (r & 7)] = av[j];
-                    }
+                    for (int e = 0; e < 4; ++e) a2[e] = __hmul2(a2[e], s2[e]);
+                    arow[j ^ (r & 7)] = av[j];
                 }
                 ptx::fence_proxy_async_smem();       // the rescaled tile must be visible to the tensor core's async proxy
                 __syncwarp();
@@ -1065,7 +1055,8 @@ bool gemm_can_scale_a(int64_t M, int64_t N, int64_t K, int rows_per_sample) {
     const int P = rows_per_sample;
     if (off || P <= 0 || !gemm_use_cg2(M) || K % GEMM_BLOCK_K != 0) return false;
     if (!(P >= GEMM_BLOCK_M ? P % GEMM_BLOCK_M == 0 : (GEMM_BLOCK_M % P == 0 && GEMM_BLOCK_M / P <= 8))) return false;
-    return gemm_pick_block_n(M, N, K) >= 128;
+    // 256-wide tiles only: a k-block of a 128-wide tile lasts 256 tensor cycles, less than the rescale of its A tile takes
+    return gemm_pick_block_n(M, N, K) == 256;
 }
 
 int gemm_pick_block_n(int64_t M, int64_t N, int64_t K, bool allow_cg2) {

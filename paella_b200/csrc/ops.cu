@@ -378,149 +378,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 320 ? 2 : 1)) dwconv3_ln_patch_
     }
 }
 
-// ------------------------------------------------------------------ depthwise 3x3 conv + LayerNorm, channel slabs through shared memory
-// The two kernels above re-load every input through L1 (9 or 2.5 loads per output float4) and are bound by load issue and
-// latency at 27-38 % occupancy (ncu, round 1: 2 TB/s of 6.5).  Here a CTA owns a 2 x 8 patch of positions for ALL channels,
-// but walks the channels in slabs of 64: each slab's 4 x 10 input halo (and its 9 x 64 filter taps) is brought in ONCE by
-// cp.async into a double-buffered shared-memory tile (zero-filled outside the image = the conv's zero padding), so global
-// memory sees plain 256/512-byte row segments and the 9-tap reuse is served by shared memory.  Thread = (position, 4-channel
-// quad of the slab): it keeps its position's outputs of every slab in registers (NS float4), so the LayerNorm over all
-// channels is an in-thread sum + a 16-lane shuffle reduction -- no shared-memory reduction, no extra __syncthreads.
-// With a skip tensor, output channel g reads concatenated [x, skip] channels 2g, 2g+1: a slab of 64 outputs reads 128
-// contiguous input channels of ONE of the two tensors (c % 128 == 0).
-__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void* gsrc, bool valid) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(valid ? 16u : 0u) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-constexpr int DWS_HALO = (DW_PH + 2) * (DW_PW + 2);        // 40 input positions per patch
-
-template <int NS, bool SKIP>
-__global__ void __launch_bounds__(256, 2) dwconv3_ln_slab_kernel(const float* __restrict__ x, const float* __restrict__ skip,
-                                                                 const float* __restrict__ wp, const float* __restrict__ bias,
-                                                                 int B, int h, int w, __half* __restrict__ out) {
-    constexpr int C = NS * 64;
-    constexpr int CIN = SKIP ? 128 : 64;                   // input channels per slab
-    constexpr int TILE_F = DWS_HALO * CIN;                 // floats of one halo tile
-    constexpr int W_F = 9 * CIN;                           // floats of one slab's taps ([tap][per][64] as packed)
-    extern __shared__ __align__(16) float dws_smem[];      // 2 x (TILE_F + W_F)
-    pdl_launch_dependents();
-    const int tid = threadIdx.x;
-    const int pos = tid >> 4, quad = tid & 15;
-    const int oy = pos / DW_PW, ox = pos % DW_PW;
-    const int tiles_x = (w + DW_PW - 1) / DW_PW, tiles_y = (h + DW_PH - 1) / DW_PH;
-    const int b = blockIdx.x / (tiles_x * tiles_y);
-    const int tr = blockIdx.x - b * (tiles_x * tiles_y);
-    const int y0 = (tr / tiles_x) * DW_PH, x0 = (tr % tiles_x) * DW_PW;
-
-    auto load_slab = [&](int s, int buf) {
-        float* tile = dws_smem + buf * (TILE_F + W_F);
-        float* wt = tile + TILE_F;
-        // concatenated input channels [CIN*s, CIN*s + CIN) of cat[x, skip] live in one tensor
-        const float* src = x;
-        int c0 = CIN * s;
-        if (SKIP && c0 >= C) { src = skip; c0 -= C; }
-        constexpr int CH16 = CIN / 4;                      // 16-byte chunks per position
-        for (int i = tid; i < DWS_HALO * CH16; i += 256) {
-            const int hp = i / CH16, ch = i - hp * CH16;
-            const int iy = y0 - 1 + hp / (DW_PW + 2), ix = x0 - 1 + hp % (DW_PW + 2);
-            const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
-            const float* g = src + (((int64_t)b * h + (ok ? iy : 0)) * w + (ok ? ix : 0)) * C + c0 + ch * 4;
-            cp_async16_zfill(smem_u32(tile + hp * CIN + ch * 4), g, ok);
-        }
-        // taps: packed [9][per][C] -> shared [9][per][64]
-        constexpr int PER = SKIP ? 2 : 1;
-        for (int i = tid; i < 9 * PER * 16; i += 256) {
-            const int tp = i / 16, q = i - tp * 16;       // tp = tap * PER + j
-            cp_async16_zfill(smem_u32(wt + tp * 64 + q * 4), wp + (int64_t)tp * C + 64 * s + q * 4, true);
-        }
-    };
-
-    float4 acc[NS];
-    load_slab(0, 0);
-    cp_async_commit_group();
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        const int buf = s & 1;
-        if (s + 1 < NS) load_slab(s + 1, buf ^ 1);
-        cp_async_commit_group();
-        cp_async_wait_group<1>();                          // slab s has landed (slab s+1 may still be in flight)
-        __syncthreads();
-        const float* tile = dws_smem + buf * (TILE_F + W_F);
-        const float* wt = tile + TILE_F;
-        float4 a = __ldg(reinterpret_cast<const float4*>(bias + 64 * s) + quad);
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const float* vp = tile + ((oy + ky) * (DW_PW + 2) + ox + kx) * CIN;
-                const int tap = ky * 3 + kx;
-                if (!SKIP) {
-                    const float4 v = *reinterpret_cast<const float4*>(vp + quad * 4);
-                    const float4 ww = *reinterpret_cast<const float4*>(wt + tap * 64 + quad * 4);
-                    a.x = fmaf(v.x, ww.x, a.x); a.y = fmaf(v.y, ww.y, a.y); a.z = fmaf(v.z, ww.z, a.z); a.w = fmaf(v.w, ww.w, a.w);
-                } else {
-                    const float4 v0 = *reinterpret_cast<const float4*>(vp + quad * 8), v1 = *reinterpret_cast<const float4*>(vp + quad * 8 + 4);
-                    const float4 wa = *reinterpret_cast<const float4*>(wt + (tap * 2 + 0) * 64 + quad * 4);
-                    const float4 wb = *reinterpret_cast<const float4*>(wt + (tap * 2 + 1) * 64 + quad * 4);
-                    a.x = fmaf(v0.x, wa.x, fmaf(v0.y, wb.x, a.x));
-                    a.y = fmaf(v0.z, wa.y, fmaf(v0.w, wb.y, a.y));
-                    a.z = fmaf(v1.x, wa.z, fmaf(v1.y, wb.z, a.z));
-                    a.w = fmaf(v1.z, wa.w, fmaf(v1.w, wb.w, a.w));
-                }
-            }
-        acc[s] = a;
-        __syncthreads();                                   // everyone is done with this buffer before it is refilled
-    }
-    // ---- LayerNorm over the C channels of this thread's position: in-thread over slabs, then over the 16 quads (lanes)
-    float s1 = 0.f;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) s1 += (acc[s].x + acc[s].y) + (acc[s].z + acc[s].w);
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    const float mean = s1 * (1.0f / C);
-    float s2 = 0.f;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        const float d0 = acc[s].x - mean, d1 = acc[s].y - mean, d2 = acc[s].z - mean, d3 = acc[s].w - mean;
-        s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    const float rstd = ln_rstd(s2 * (1.0f / C));
-    const int y = y0 + oy, xx = x0 + ox;
-    if (y < h && xx < w) {
-        __half* o = out + (((int64_t)b * h + y) * w + xx) * C + quad * 4;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            uint2 pk;
-            pk.x = pack_half2((acc[s].x - mean) * rstd, (acc[s].y - mean) * rstd);
-            pk.y = pack_half2((acc[s].z - mean) * rstd, (acc[s].w - mean) * rstd);
-            *reinterpret_cast<uint2*>(o + 64 * s) = pk;
-        }
-    }
-}
-
-template <int NS>
-static int dwconv3_slab_launch(const float* x, const float* skip, const float* wp, const float* bias, int B, int h, int w,
-                               __half* out, cudaStream_t st) {
-    const int64_t grid = (int64_t)B * ceil_div(h, DW_PH) * ceil_div(w, DW_PW);
-    PB_CHECK(grid < (1ll << 31), "dwconv: grid too large");
-    if (skip) {
-        constexpr int SMEM = 2 * (DWS_HALO * 128 + 9 * 128) * 4;
-        static DeviceOnce once;
-        if (once.first()) PB_CUDA(cudaFuncSetAttribute(dwconv3_ln_slab_kernel<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        dwconv3_ln_slab_kernel<NS, true><<<(unsigned)grid, 256, SMEM, st>>>(x, skip, wp, bias, B, h, w, out);
-    } else {
-        constexpr int SMEM = 2 * (DWS_HALO * 64 + 9 * 64) * 4;
-        dwconv3_ln_slab_kernel<NS, false><<<(unsigned)grid, 256, SMEM, st>>>(x, skip, wp, bias, B, h, w, out);
-    }
-    PB_LAUNCH_CHECK();
-    return 0;
-}
-
 static int dwconv3_patch_launch(const float* x, const float* skip, const float* wp, const float* bias, int B, int h, int w,
                                 int c, __half* out, cudaStream_t st) {
     const int64_t grid = (int64_t)B * ceil_div(h, DW_PH) * ceil_div(w, DW_PW);
@@ -564,12 +421,6 @@ int launch_dwconv_ln(const float* x, const float* skip, const float* w_packed, c
     // measured (ncu, B200): the patch kernel wins at 8192 x 1280 (32.6 vs 39.6 us) and loses at 32768 x 640
     // (99 vs 62 us: 152 registers x 160 threads leaves 15% occupancy), so it takes the wide levels only
     static const bool patch_all = getenv("PB200_DWCONV_PATCH") != nullptr;
-    static const bool no_slab = getenv("PB200_DWCONV_NOSLAB") != nullptr;      // A/B knob
-    if (k == 3 && !old_kernel && !patch_all && !no_slab && (!skip || c % 128 == 0)) {
-        if (c == 640) return dwconv3_slab_launch<10>(x, skip, w_packed, bias, B, h, w, out, st);
-        if (c == 1280) return dwconv3_slab_launch<20>(x, skip, w_packed, bias, B, h, w, out, st);
-        if (c == 128) return dwconv3_slab_launch<2>(x, skip, w_packed, bias, B, h, w, out, st);
-    }
     if (k == 3 && c <= 2560 && !old_kernel && (patch_all || (c > 640 && w >= DW_PW)))
         return dwconv3_patch_launch(x, skip, w_packed, bias, B, h, w, c, out, st);
     if (c <= 128) return dwconv_dispatch<1>(x, skip, w_packed, bias, B, h, w, c, k, out, st);

@@ -17,7 +17,7 @@
 
 namespace pb {
 
-enum VqPack { VP_COPY_F32, VP_CAST_F16, VP_DW9, VP_CONV4, VP_CONVT4 };
+enum VqPack { VP_COPY_F32, VP_CAST_F16, VP_DW9, VP_CONV4, VP_CONVT4, VP_T12 };
 
 __global__ void vq_pack_kernel(const float* __restrict__ src, void* __restrict__ dst, int kind, int64_t n, int d0, int d1,
                                int d2) {
@@ -31,6 +31,11 @@ __global__ void vq_pack_kernel(const float* __restrict__ src, void* __restrict__
         case VP_DW9: {      // src [c=d0, 1, 3, 3] -> dst [9][c]
             const int c = d0, ch = (int)(i % c), tap = (int)(i / c);
             d32[i] = src[(int64_t)ch * 9 + tap];
+            break;
+        }
+        case VP_T12: {      // src [c0=d0, 12] -> dst [12][c0]: the in_block kernel's lanes read consecutive output channels
+            const int c0 = d0, co = (int)(i % c0), k = (int)(i / c0);
+            d32[i] = src[(int64_t)co * 12 + k];
             break;
         }
         case VP_CONV4: {    // src [Cout=d0, Cin=d1, 4, 4] -> dst fp16 [Cout][16][Cpad=d2] (zero padded channels)
@@ -73,16 +78,15 @@ __global__ void __launch_bounds__(256) vq_in_block_kernel(const float* __restric
 #pragma unroll
         for (int d = 0; d < 4; ++d)
             in[c * 4 + d] = img[(((int64_t)b * 3 + c) * H + 2 * y + (d >> 1)) * W + 2 * x + (d & 1)];
-    float o[4];
+    // w is packed [12][c0] (VP_T12): one coalesced float4 per input tap (round 2 first had [c0][12]: 48 loads per thread,
+    // each touching 32 different lines per warp -- 4.7 ms for 64 images, 35x the time of the 805 MB store it feeds)
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + q);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int co = q * 4 + j;
-        float acc = bias[co];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) acc = fmaf(in[k], __ldg(w + co * 12 + k), acc);
-        o[j] = acc;
+    for (int k = 0; k < 12; ++k) {
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (int64_t)k * c0) + q);
+        acc.x = fmaf(in[k], ww.x, acc.x); acc.y = fmaf(in[k], ww.y, acc.y); acc.z = fmaf(in[k], ww.z, acc.z); acc.w = fmaf(in[k], ww.w, acc.w);
     }
-    *reinterpret_cast<float4*>(out + pos * c0 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(out + pos * c0 + q * 4) = acc;
 }
 
 // out_block: Conv2d(c0 -> 12, k=1) + PixelShuffle(2).  x NHWC fp32 [B,h2,w2,c0] -> img NCHW [B,3,2h2,2w2]; warp per position.
@@ -363,23 +367,6 @@ static void conv_tile(int gw, int& tw, int& th) {
 
 }  // namespace pb
 
-namespace pb {
-// Images per pass through the codec.  All of one pass's activations (x, LayerNorm scratch, fp16 operands, the 4c-wide MLP
-// hidden: ~28 MB per 256x256 image at the bottleneck) should stay L2-resident from the kernel that writes them to the kernel
-// that reads them; a whole batch streams every intermediate through HBM instead.  PB200_VQ_SUBBATCH overrides (0 = whole batch).
-static int vq_sub_batch(int batch, int img_h, int img_w) {
-    static const char* env = getenv("PB200_VQ_SUBBATCH");
-    int n = env ? atoi(env) : -1;
-    if (n < 0) {
-        const double per_img = (double)(img_h / 4) * (img_w / 4) * 7168.0;      // bytes of bottleneck activations per image
-        n = (int)(96.0e6 / per_img);
-        if (n < 1) n = 1;
-    }
-    return (n == 0 || n > batch) ? batch : n;
-}
-
-}  // namespace pb
-
 extern "C" {
 
 int64_t pb200_vqgan_resblock_workspace_bytes(int batch, int h, int w, int c) {
@@ -427,7 +414,7 @@ int pb200_vqgan_create(const pb200_vqgan_config* cfg, pb200_vqgan** out) {
     m->cpad0 = (m->c0 + 63) / 64 * 64;
     m->cpad1 = (m->c1 + 63) / 64 * 64;
     const int c0 = m->c0, c1 = m->c1, cl = cfg->c_latent;
-    m->in_w = m->f32("in_block.1.weight", (int64_t)c0 * 12);
+    m->in_w = m->add("in_block.1.weight", (int64_t)c0 * 12, VP_T12, (int64_t)c0 * 12, 4, c0);
     m->in_b = m->f32("in_block.1.bias", c0);
     m->add_resblock("down_blocks.0.", c0, m->enc0);
     m->down_w = m->add("down_blocks.1.weight", (int64_t)c1 * c0 * 16, VP_CONV4, (int64_t)c1 * 16 * m->cpad0, 2, c1, c0, m->cpad0);
@@ -503,26 +490,10 @@ int64_t pb200_vqgan_workspace_bytes(const pb200_vqgan* m, int batch, int img_h, 
     return off + 256;
 }
 
-static int vq_encode_pass(pb200_vqgan* m, const float* img, int batch, int img_h, int img_w, float* latents_nchw,
-                          float* quantised_nchw, int64_t* indices, void* workspace, int64_t workspace_bytes, void* stream);
-
 int pb200_vqgan_encode(pb200_vqgan* m, const float* img, int batch, int img_h, int img_w, float* latents_nchw,
                        float* quantised_nchw, int64_t* indices, void* workspace, int64_t workspace_bytes, void* stream) {
     PB_CHECK(m->blob != nullptr, "encode: weights not bound");
     if (m->host_params_stale) PB_TRY(pb200_vqgan_sync_params(m, stream));
-    const int sub = vq_sub_batch(batch, img_h, img_w);
-    const int64_t lat = (int64_t)m->cfg.c_latent * (img_h / 4) * (img_w / 4);
-    for (int b0 = 0; b0 < batch; b0 += sub) {
-        const int nb = batch - b0 < sub ? batch - b0 : sub;
-        PB_TRY(vq_encode_pass(m, img + (int64_t)b0 * 3 * img_h * img_w, nb, img_h, img_w, latents_nchw ? latents_nchw + b0 * lat : nullptr,
-                              quantised_nchw ? quantised_nchw + b0 * lat : nullptr,
-                              indices ? indices + (int64_t)b0 * (img_h / 4) * (img_w / 4) : nullptr, workspace, workspace_bytes, stream));
-    }
-    return 0;
-}
-
-static int vq_encode_pass(pb200_vqgan* m, const float* img, int batch, int img_h, int img_w, float* latents_nchw,
-                          float* quantised_nchw, int64_t* indices, void* workspace, int64_t workspace_bytes, void* stream) {
     PB_CHECK(img_h % 4 == 0 && img_w % 4 == 0, "encode: image %dx%d not divisible by 4", img_h, img_w);
     PB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -585,29 +556,11 @@ int pb200_vqgan_decode(pb200_vqgan* m, const int64_t* indices, const float* late
     return pb200_vqgan_decode_ex(m, indices, latents_nchw, batch, h, w, img, PB200_IMG_F32_NCHW, workspace, workspace_bytes, stream);
 }
 
-static int vq_decode_pass(pb200_vqgan* m, const int64_t* indices, const float* latents_nchw, int batch, int h, int w, void* img,
-                          int img_mode, void* workspace, int64_t workspace_bytes, void* stream);
-
 int pb200_vqgan_decode_ex(pb200_vqgan* m, const int64_t* indices, const float* latents_nchw, int batch, int h, int w, void* img,
                           int img_mode, void* workspace, int64_t workspace_bytes, void* stream) {
     PB_CHECK(m->blob != nullptr, "decode: weights not bound");
     PB_CHECK(img_mode >= 0 && img_mode <= 2, "decode: unknown image mode %d", img_mode);
     if (m->host_params_stale) PB_TRY(pb200_vqgan_sync_params(m, stream));
-    const int sub = vq_sub_batch(batch, 4 * h, 4 * w);
-    const int64_t px = (int64_t)16 * h * w * 3;          // output elements per image
-    for (int b0 = 0; b0 < batch; b0 += sub) {
-        const int nb = batch - b0 < sub ? batch - b0 : sub;
-        void* out = img_mode == PB200_IMG_U8_NHWC ? (void*)(reinterpret_cast<uint8_t*>(img) + b0 * px)
-                                                  : (void*)(reinterpret_cast<float*>(img) + b0 * px);
-        PB_TRY(vq_decode_pass(m, indices ? indices + (int64_t)b0 * h * w : nullptr,
-                              latents_nchw ? latents_nchw + (int64_t)b0 * m->cfg.c_latent * h * w : nullptr, nb, h, w, out, img_mode,
-                              workspace, workspace_bytes, stream));
-    }
-    return 0;
-}
-
-static int vq_decode_pass(pb200_vqgan* m, const int64_t* indices, const float* latents_nchw, int batch, int h, int w, void* img,
-                          int img_mode, void* workspace, int64_t workspace_bytes, void* stream) {
     PB_CHECK((indices != nullptr) != (latents_nchw != nullptr), "decode: pass indices or latents, not both");
     PB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;

@@ -259,12 +259,6 @@ class TimestepBlock(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
-# A/B knob: run guided steps in groups of this many (cond, uncond) pairs so that a block's activations stay L2-resident
-# (0 = whole batch at once).  See Paella._features_chunked.
-_SUBBATCH_PAIRS = int(os.environ.get("PB200_SUBBATCH", "0") or 0)
-_SUBBATCH_STREAMS = int(os.environ.get("PB200_STREAMS", "1") or 1)
-
-
 class ConditioningCache:
     """x- and t-independent conditioning work of one sample() call: c_embed and every AttnBlock's
     cond K/V for ``batch_total`` samples (conditional rows first, then unconditional rows)."""
@@ -347,7 +341,6 @@ class Paella(nn.Module):
         self._packed_key = None
         self._workspace = None
         self._cond_single = None
-        self._side_streams = None
 
     # -------------------------------------------------------------- initialisation (ref/src/modules.py:189-210)
     def _reference_init(self, blocks, num_labels):
@@ -488,7 +481,7 @@ class Paella(nn.Module):
 
     def _ws(self, nbytes: int) -> torch.Tensor:
         """Scratch for the launches of ONE stream (the library bump-allocates it identically on every call): one buffer per
-        CUDA stream the model is driven from, so concurrent sub-batches (Paella._features_chunked) never share scratch."""
+        CUDA stream the model is driven from, so calls issued on different streams never share scratch."""
         if not isinstance(self._workspace, dict):
             self._workspace = {}
         key = torch.cuda.current_stream(self._device()).cuda_stream
@@ -622,9 +615,6 @@ class Paella(nn.Module):
             Bt *= 2
         if Bt != cond.batch_total:
             raise PaellaB200Error(f"batch {Bt} does not match the conditioning cache ({cond.batch_total})")
-        chunk = _SUBBATCH_PAIRS if cfg_pairs else 0
-        if chunk and x.shape[0] > chunk:
-            return self._features_chunked(x, r, cond, attn_weights, attn_weights_batch, chunk)
         with torch.cuda.device(dev):
             x = x.to(device=dev, dtype=torch.int64).contiguous()
             r = r.to(device=dev, dtype=torch.float32).contiguous()
@@ -636,44 +626,6 @@ class Paella(nn.Module):
                                           aw.numel() if aw is not None else 0, attn_weights_batch, ptr(feats), ptr(ws),
                                           ws.numel(), current_stream()), "pb200_paella_features")
         return feats
-
-    def _features_chunked(self, x, r, cond: ConditioningCache, attn_weights, attn_weights_batch, chunk: int) -> torch.Tensor:
-        """The CFG batch in groups of ``chunk`` (cond, uncond) pairs, each group through the whole denoiser on its own.  Samples
-        are independent, so this is the same arithmetic; the point is the working set: at 2 x 64 samples one level-1 block
-        touches x 42 MB + hidden 84 MB + qkv 63 MB, more than the 126 MB L2, so every kernel re-reads its input from HBM;
-        half the batch keeps a block's tensors L2-resident from the kernel that writes them to the one that reads them."""
-        dev = self._device()
-        B, H, W = x.shape
-        n_tok = H * W
-        full = torch.empty(2 * B * n_tok, self._cfg["c_out"], dtype=torch.float32, device=dev)
-        maps = cond.__dict__.setdefault("_chunk_maps", {})
-        main = torch.cuda.current_stream(dev)
-        side = []
-        if _SUBBATCH_STREAMS > 1:       # groups are independent: run them on their own streams so that one group's launch gaps,
-            if getattr(self, "_side_streams", None) is None or len(self._side_streams) != _SUBBATCH_STREAMS:      # tails and memory-
-                self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(_SUBBATCH_STREAMS)]           # bound kernels
-            side = self._side_streams                                                                             # overlap the other's
-        for i, lo in enumerate(range(0, B, chunk)):
-            hi = min(B, lo + chunk)
-            key = (lo, hi, B)
-            if key not in maps:
-                base = cond.slot_map if cond.slot_map is not None else torch.arange(2 * B, dtype=torch.int32, device=dev)
-                maps[key] = torch.cat([base[lo:hi], base[B + lo:B + hi]]).contiguous()
-            sub = ConditioningCache(cond.cache, 2 * (hi - lo), cond.s_max, cond.slots, maps[key])
-            aw_b = max(0, min(attn_weights_batch, hi) - lo) if attn_weights is not None else 0
-            st = side[i % len(side)] if side else main
-            if side:
-                st.wait_stream(main)
-            with torch.cuda.stream(st):
-                f = self.features(x[lo:hi], r[lo:hi], sub, attn_weights, aw_b, cfg_pairs=True)
-                n = (hi - lo) * n_tok
-                full[lo * n_tok:hi * n_tok] = f[:n]
-                full[(B + lo) * n_tok:(B + hi) * n_tok] = f[n:]
-                if side:
-                    f.record_stream(st)
-        for st in side:
-            main.wait_stream(st)
-        return full
 
     def logits_from_features(self, feats: torch.Tensor, batch: int, h: int, w: int) -> torch.Tensor:
         L = lib()
@@ -695,6 +647,7 @@ class Paella(nn.Module):
             ws = self._ws(L.pb200_paella_workspace_bytes(self._handle, batch, h, w, 1))
             n = batch * h * w
             chunks = ops.philox_row_chunks(n, self.num_labels)       # one kernel per 32-bit-indexable piece, like torch
+            ops.skip_philox_for_split(chunks, n * self.num_labels, dev, generator)
             flat = out.view(-1)
             for lo, hi in chunks:
                 seed, off = ops.take_philox((hi - lo) * self.num_labels, dev, generator)

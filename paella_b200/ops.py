@@ -34,9 +34,11 @@ def philox_row_chunks(rows: int, k: int, elem_bytes: int = 4):
     """Row ranges [(lo, hi), ...] over which torch runs ONE distribution kernel each for a contiguous [rows, k] tensor.
     TensorIterator splits an iteration space that is not 32-bit indexable (numel > INT32_MAX or last BYTE offset >
     INT32_MAX, i.e. > 2^29 fp32 elements) into halves, first half first, recursively (ATen TensorIterator::split /
-    SplitUntil32Bit, DistributionTemplates.h:132-138); every sub-kernel takes its own Philox offset from the generator.
-    bs=64 at 32x32x8192 is exactly 2^29 elements (one kernel); larger batches split -- mirrored here so the draws stay
-    bit-identical to torch.multinomial's."""
+    SplitUntil32Bit, DistributionTemplates.h:132-138); every sub-kernel takes its own Philox offset from the generator --
+    and the ROOT call has already taken one for the whole tensor before it notices that it must split (it computes its
+    execution policy and calls philox_cuda_state first; measured on B200: a 2^30-element draw advances the offset by
+    inc(2^30) + 2 inc(2^29)), see ``skip_philox_for_split``.  bs=64 at 32x32x8192 is exactly 2^29 elements (one kernel);
+    larger batches split -- mirrored here so the draws stay bit-identical to torch.multinomial's."""
     lim = 2 ** 31 - 1
 
     def split(n):
@@ -52,6 +54,12 @@ def philox_row_chunks(rows: int, k: int, elem_bytes: int = 4):
         out.append((lo, lo + n // k))
         lo += n // k
     return out
+
+
+def skip_philox_for_split(chunks, total_numel: int, device, generator=None) -> None:
+    """Consume the offset increment torch's root distribution call takes (and never uses) when the tensor has to be split."""
+    if len(chunks) > 1:
+        take_philox(total_numel, device, generator)
 
 
 # ------------------------------------------------------------------ random ops
@@ -75,7 +83,9 @@ def multinomial(p: torch.Tensor, generator=None) -> torch.Tensor:
     assert p.dim() == 2 and p.dtype == torch.float32
     p = p.contiguous()
     out = torch.empty(p.shape[0], dtype=torch.int64, device=p.device)
-    for lo, hi in philox_row_chunks(p.shape[0], p.shape[1]):
+    chunks = philox_row_chunks(p.shape[0], p.shape[1])
+    skip_philox_for_split(chunks, p.numel(), p.device, generator)
+    for lo, hi in chunks:
         seed, off = take_philox((hi - lo) * p.shape[1], p.device, generator)
         check(lib().pb200_multinomial(ptr(p[lo:hi]), hi - lo, p.shape[1], seed, off, ptr(out[lo:hi]), current_stream()),
               "pb200_multinomial")
@@ -92,6 +102,7 @@ def resample_logits(logits_c: torch.Tensor, logits_u: Optional[torch.Tensor], cf
     out = torch.empty((B,) + tuple(logits_c.shape[2:]), dtype=torch.int64, device=lc.device)
     m = {"multinomial": 0, "argmax": 1}[mode]
     chunks = philox_row_chunks(B * hw, K) if m == 0 else [(0, B * hw)]
+    skip_philox_for_split(chunks, B * hw * K, lc.device, generator)
     for lo, hi in chunks:
         if lo % hw or hi % hw:
             raise _lib.PaellaB200Error("resample_logits: torch's 32-bit split of this draw falls inside a sample")

@@ -251,28 +251,6 @@ def test_forward_memoises_conditioning_for_the_reference_loop(default_model):
     assert torch.equal(c, d)
 
 
-@pytest.mark.parametrize("pairs,streams", [(2, 1), (2, 2), (3, 2)])
-def test_sub_batched_features_are_bit_identical(default_model, monkeypatch, pairs, streams):
-    """The L2-residency knob (PB200_SUBBATCH / PB200_STREAMS): the CFG batch in groups of pairs, optionally on side streams with
-    their own workspaces, is the same arithmetic per sample -- features must be bit-identical to the whole-batch run
-    (fixed K-order accumulation in TMEM, integer-atomic GRN / LayerNorm statistics), incl. a ragged last group."""
-    from paella_b200 import modules
-    from paella_b200.synth import synthetic_conditioning
-    m, _ = default_model
-    B, H = 5, 16
-    cond, uncond = synthetic_conditioning(B, 24, device=DEV)
-    cache = m.prepare_conditioning([cond, uncond], (H, H))
-    x = torch.randint(0, 8192, (B, H, H), device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
-    r = torch.linspace(0.9, 0.1, B, device=DEV)
-    monkeypatch.setattr(modules, "_SUBBATCH_PAIRS", 0)
-    want = m.features(x, r, cache, cfg_pairs=True)
-    monkeypatch.setattr(modules, "_SUBBATCH_PAIRS", pairs)
-    monkeypatch.setattr(modules, "_SUBBATCH_STREAMS", streams)
-    got = m.features(x, r, cache, cfg_pairs=True)
-    torch.cuda.synchronize()
-    assert torch.equal(got, want)
-
-
 def test_sample_distributed_options_vs_oracle_teacher_forced():
     """§8(f1): init_x, per-step cfgs (linspace), sampling_conditional_steps (later steps unguided) of
     ref/src_distributed/utils.py:97-126 — tiny golden model, every step vs the oracle from the oracle's state."""

@@ -16,12 +16,6 @@ if [ $? -ne 0 ]; then
   export PB200_NO_GRN_FOLD=1
 fi
 tail -8 gpurun_out/${TAG}_pytest_ascale.log
-timeout 600 python -m pytest tests/test_gpu_blocks.py -k "resblock" -q --no-header -rf -p no:cacheprovider > gpurun_out/${TAG}_pytest_dwslab.log 2>&1
-if [ $? -ne 0 ]; then
-  echo "resblock tests FAILED with the slab dwconv kernel: rest of the round runs with PB200_DWCONV_NOSLAB=1" | tee gpurun_out/${TAG}_dwslab_fallback.txt
-  export PB200_DWCONV_NOSLAB=1
-fi
-tail -8 gpurun_out/${TAG}_pytest_dwslab.log
 timeout 600 python -m pytest tests/test_gpu_parity_r2.py -k "vqgan_resblock" -q --no-header -rf -p no:cacheprovider > gpurun_out/${TAG}_pytest_vqmlp.log 2>&1
 if [ $? -ne 0 ]; then
   echo "codec ResBlock tests FAILED with the fused MLP kernel: rest of the round runs with PB200_VQ_MLP_UNFUSED=1" | tee gpurun_out/${TAG}_vqmlp_fallback.txt
