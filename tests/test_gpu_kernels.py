@@ -258,15 +258,20 @@ def test_gemm_resid_film_inplace(M, N, K, P):
     assert err < 1e-4          # measured <= 2.1e-5
 
 
-@pytest.mark.parametrize("M,N,K,P", [(8192, 1280, 5120, 64), (2048, 1280, 5120, 16), (16384, 640, 2560, 256), (8256, 1280, 640, 64),
-                                     (512, 256, 128, 128), (4096, 1280, 5120, 32)])
+@pytest.mark.parametrize("M,N,K,P", [(8192, 1280, 5120, 64), (2048, 1280, 5120, 16), (8256, 1280, 640, 64), (16384, 1280, 5120, 256),
+                                     (8192, 1280, 5120, 128), (8192, 1280, 5120, 32)])
 def test_gemm_a_scale_equals_gemm_on_prescaled_a(M, N, K, P):
     """GlobalResponseNorm folded into GEMM2's A operand (pb200_gemm_epilogue::a_scale): multiplying the A tile by the
     per-(sample, k) fp16 factors in shared memory (one HMUL2 rounding, = the fp16 product) must give EXACTLY what the same
     kernel gives on an A matrix pre-multiplied the same way -- same MMAs, same accumulation order.  Shapes: the level-1 / level-2
-    / level-0 MLP GEMM2 of the bench, a ragged last tile, one sample per tile, and a half-batch."""
+    MLP GEMM2 of the bench, a ragged last tile, samples spanning two tiles, one and four samples per 128-row tile.  (The fold
+    is built for the 2-SM kernel's 256-wide tiles only: a 128-wide tile's k-block is shorter than the rescale of its A tile.)"""
+    import ctypes
     from paella_b200 import _lib
     ops = _ops()
+    bn, two_sm, tail = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.lib().pb200_gemm_plan(M, N, K, 0, ctypes.byref(bn), ctypes.byref(two_sm), ctypes.byref(tail)), "gemm_plan")
+    assert bn.value == 256 and two_sm.value == 1, "shape no longer planned on 256-wide 2-SM tiles: pick another for this test"
     g = torch.Generator(device=DEV).manual_seed(21)
     a = torch.randn(M, K, device=DEV, generator=g).half()
     w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).half()
