@@ -1055,8 +1055,11 @@ bool gemm_can_scale_a(int64_t M, int64_t N, int64_t K, int rows_per_sample) {
     const int P = rows_per_sample;
     if (off || P <= 0 || !gemm_use_cg2(M) || K % GEMM_BLOCK_K != 0) return false;
     if (!(P >= GEMM_BLOCK_M ? P % GEMM_BLOCK_M == 0 : (GEMM_BLOCK_M % P == 0 && GEMM_BLOCK_M / P <= 8))) return false;
-    // 256-wide tiles only: a k-block of a 128-wide tile lasts 256 tensor cycles, less than the rescale of its A tile takes
-    return gemm_pick_block_n(M, N, K) == 256;
+    // 256-wide tiles only: a k-block of a 128-wide tile lasts 256 tensor cycles, less than the rescale of its A tile took with two
+    // transform warps (PB200_GRN_FOLD_128=1 lets 128-wide tiles fold too: experiment knob for the four-warp version)
+    static const bool allow128 = getenv("PB200_GRN_FOLD_128") != nullptr;
+    const int bn = gemm_pick_block_n(M, N, K);
+    return bn == 256 || (allow128 && bn == 128);
 }
 
 int gemm_pick_block_n(int64_t M, int64_t N, int64_t K, bool allow_cg2) {
