@@ -1051,9 +1051,8 @@ static bool gemm_use_cg2(int64_t M) {
 }
 
 bool gemm_can_scale_a(int64_t M, int64_t N, int64_t K, int rows_per_sample) {
-    static const bool off = getenv("PB200_NO_GRN_FOLD") != nullptr;      // A/B knob
     const int P = rows_per_sample;
-    if (off || P <= 0 || !gemm_use_cg2(M) || K % GEMM_BLOCK_K != 0) return false;
+    if (P <= 0 || !gemm_use_cg2(M) || K % GEMM_BLOCK_K != 0) return false;
     if (!(P >= GEMM_BLOCK_M ? P % GEMM_BLOCK_M == 0 : (GEMM_BLOCK_M % P == 0 && GEMM_BLOCK_M / P <= 8))) return false;
     // 256-wide tiles only: a k-block of a 128-wide tile lasts 256 tensor cycles, less than the rescale of its A tile took with two
     // transform warps (PB200_GRN_FOLD_128=1 lets 128-wide tiles fold too: experiment knob for the four-warp version)

@@ -759,7 +759,11 @@ int pb200_paella_features(pb200_paella* m, const int64_t* tokens, const float* r
                 PB_TRY(m->gemm(ws.a16, ch, M, ch, b.w1, 4 * (int64_t)ch, e1, st));
                 // GlobalResponseNorm: folded into GEMM2's A operand where its tiles line up with the samples (multipliers only,
                 // shift pushed into the bias), else applied to the hidden in place
-                const bool fold_grn = gemm_can_scale_a(M, ch, 4 * (int64_t)ch, P);
+                // Measured on B200 (profiles/r02_ab_notes.md): the fold removes the 168 MB GRN pass (-12.4 ms per bench step) but the
+                // in-place rescale adds 32 KB of shared-memory traffic per k-block to a 2-SM main loop whose operand reads already
+                // use ~3/4 of the 128 B/clk port: GEMM2 61 -> 89 us per level-1 launch (+17 ms per step).  Net loss: opt-in.
+                static const bool fold_on = getenv("PB200_GRN_FOLD") != nullptr;
+                const bool fold_grn = fold_on && gemm_can_scale_a(M, ch, 4 * (int64_t)ch, P);
                 __half* grn_s16 = reinterpret_cast<__half*>(ws.grn_mult);
                 if (fold_grn)
                     PB_TRY(launch_grn_scale_f16(Bc, 4 * ch, stat, stat_next, 4 * m->max_c, m->w<float>(b.gamma), grn_s16, st));

@@ -45,12 +45,19 @@ struct MlpSmem {
     static constexpr int N2B = C - N2A;
 };
 
+enum { MR_TMA = 0, MR_MMA = 1, MR_GELU = 2 };
+enum { ME_A_ISSUE = 0, ME_W1_ISSUE, ME_W2_ISSUE, ME_A_READY, ME_G1_GO, ME_G1_ISSUED, ME_G2_GO, ME_G2_ISSUED, ME_ACC1_READY, ME_GELU_DONE,
+       ME_H_FREE, ME_H_WRITTEN, ME_ACC2_READY, ME_TILE_DONE };
+const char* const kMlpRoles[TRACE_ROLES] = {"tma", "mma", "gelu", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-"};
+const char* const kMlpEvents[] = {"a_issue", "w1_issue", "w2_issue", "a_ready", "g1_go", "g1_issued", "g2_go", "g2_issued", "acc1_ready",
+                                  "gelu_done", "h_free", "h_written", "acc2_ready", "tile_done"};
+
 // out[M, C] (fp32, in place on the residual stream) ; M rows, any M
 template <int C>
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w1,
                     const __grid_constant__ CUtensorMap tm_w2a, const __grid_constant__ CUtensorMap tm_w2b, const float* __restrict__ b1,
-                    const float* __restrict__ b2, float* __restrict__ x, float alpha, int M) {
+                    const float* __restrict__ b2, float* __restrict__ x, float alpha, int M, const TraceBuf trace) {
     using L = MlpSmem<C>;
     constexpr int NCH = 4 * C / MLP_HC;
     extern __shared__ uint8_t smem_raw[];
@@ -117,6 +124,7 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             for (int t = tile0; t < n_tiles; t += tile_step) {
                 const int m_idx = t * 256 + (int)crank * 128;
                 ptx::mbar_wait(a_empty, pa ^ 1);
+                trace_ev(trace, MR_TMA, ME_A_ISSUE, t);
                 if (leader) ptx::mbar_arrive_expect_tx(a_full, 2u * L::A_BYTES);
                 else ptx::mbar_arrive_cluster(l_a_full);
                 for (int kb = 0; kb < L::KB1; ++kb) ptx::tma_load_2d_cg2(&tm_a, l_a_full, sA + kb * 16384, kb * 64, m_idx);
@@ -124,6 +132,7 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 for (int j = 0; j < NCH; ++j) {
                     for (int kb = 0; kb < L::KB1; ++kb) {       // W1 rows [64j + 32*crank, +32), k-block kb
                         ptx::mbar_wait(w1_empty0 + 8u * s1, p1 ^ 1);
+                        if (kb == 0) trace_ev(trace, MR_TMA, ME_W1_ISSUE, j);
                         const uint32_t lf = l_w1_full0 + 8u * s1;
                         if (leader) ptx::mbar_arrive_expect_tx(w1_full0 + 8u * s1, 2u * L::W1_STAGE);
                         else ptx::mbar_arrive_cluster(lf);
@@ -132,6 +141,7 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     }
                     // W2 rows: this CTA's half of each N part, k columns [64j, +64)
                     ptx::mbar_wait(w2_empty0 + 8u * s2, p2 ^ 1);
+                    trace_ev(trace, MR_TMA, ME_W2_ISSUE, j);
                     const uint32_t lf2 = l_w2_full0 + 8u * s2;
                     if (leader) ptx::mbar_arrive_expect_tx(w2_full0 + 8u * s2, 2u * L::W2_STAGE);
                     else ptx::mbar_arrive_cluster(lf2);
@@ -159,6 +169,7 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 ptx::tc_fence_after();
                 for (int kb = 0; kb < L::KB1; ++kb) {
                     ptx::mbar_wait(w1_full0 + 8u * s1, p1);
+                    if (kb == 0 && lane == 0) trace_ev(trace, MR_MMA, ME_G1_GO, c1);
                     ptx::tc_fence_after();
                     if (lane == 0) {
                         const uint64_t da = ptx::umma_desc_kmajor_sw128(sA + kb * 16384);
@@ -167,7 +178,10 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                         for (int k = 0; k < 4; ++k)
                             ptx::umma_f16_cg2(tmem_base + (uint32_t)(C + ab * MLP_HC), da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
                         ptx::umma_commit_cg2_mcast(w1_empty0 + 8u * s1, (uint16_t)0x3);
-                        if (kb == L::KB1 - 1) ptx::umma_commit_cg2_mcast(acc1_full0 + 8u * ab, (uint16_t)0x3);
+                        if (kb == L::KB1 - 1) {
+                            ptx::umma_commit_cg2_mcast(acc1_full0 + 8u * ab, (uint16_t)0x3);
+                            trace_ev(trace, MR_MMA, ME_G1_ISSUED, c1);
+                        }
                     }
                     __syncwarp();
                     if (++s1 == MLP_S1) { s1 = 0; p1 ^= 1; }
@@ -181,6 +195,7 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 if (first) ptx::mbar_wait(acc2_empty, (((uint32_t)tiles_done) & 1u) ^ 1u);
                 ptx::tc_fence_after();
                 if (lane == 0) {
+                    trace_ev(trace, MR_MMA, ME_G2_GO, c2);
                     const uint64_t da = ptx::umma_desc_kmajor_sw128(sH + hb * L::H_BYTES);
                     const uint64_t dba = ptx::umma_desc_kmajor_sw128(sW2 + s2 * L::W2_STAGE);
                     const uint64_t dbb = ptx::umma_desc_kmajor_sw128(sW2 + s2 * L::W2_STAGE + (L::N2A / 2) * 128);
@@ -193,6 +208,7 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     ptx::umma_commit_cg2_mcast(h_empty0 + 8u * hb, (uint16_t)0x3);
                     ptx::umma_commit_cg2_mcast(w2_empty0 + 8u * s2, (uint16_t)0x3);
                     if (last) ptx::umma_commit_cg2_mcast(acc2_full, (uint16_t)0x3);
+                    trace_ev(trace, MR_MMA, ME_G2_ISSUED, c2);
                 }
                 __syncwarp();
                 if (++s2 == MLP_S2) { s2 = 0; p2 ^= 1; }
@@ -200,6 +216,7 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             };
             for (int t = tile0; t < n_tiles; t += tile_step) {
                 ptx::mbar_wait(a_full, pa);
+                if (lane == 0) trace_ev(trace, MR_MMA, ME_A_READY, t);
                 pa ^= 1;
                 gemm1(0);
                 for (int j = 1; j < NCH; ++j) {
@@ -227,6 +244,8 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 const int ab = c & 1;
                 const uint32_t ph = ((uint32_t)(c >> 1)) & 1u;
                 ptx::mbar_wait(acc1_full0 + 8u * ab, ph);
+                const bool tr = ew == 0 && lane == 0;
+                if (tr) trace_ev(trace, MR_GELU, ME_ACC1_READY, c);
                 ptx::tc_fence_after();
                 float v[16];
                 ptx::tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(C + ab * MLP_HC + slice * 16), v);
@@ -240,7 +259,9 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     v[g * 4 + 0] = gelu_erf_fast(v[g * 4 + 0] + bb.x); v[g * 4 + 1] = gelu_erf_fast(v[g * 4 + 1] + bb.y);
                     v[g * 4 + 2] = gelu_erf_fast(v[g * 4 + 2] + bb.z); v[g * 4 + 3] = gelu_erf_fast(v[g * 4 + 3] + bb.w);
                 }
+                if (tr) trace_ev(trace, MR_GELU, ME_GELU_DONE, c);
                 ptx::mbar_wait(h_empty0 + 8u * ab, ph ^ 1);                                 // GEMM2(j-2) is done with this H buffer
+                if (tr) trace_ev(trace, MR_GELU, ME_H_FREE, c);
                 uint8_t* hrow = smem_gen + L::OFF_H + ab * L::H_BYTES + r_tile * 128;
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {                // this warp's 16 columns = 16-byte chunks 2*slice, 2*slice + 1 of the row
@@ -252,9 +273,11 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive_cluster(l_h_full0 + 8u * ab);
+                if (tr) trace_ev(trace, MR_GELU, ME_H_WRITTEN, c);
             }
             // ---- final epilogue: x = x + alpha * (acc2 + b2)
             ptx::mbar_wait(acc2_full, ((uint32_t)tiles_done) & 1u);
+            if (ew == 0 && lane == 0) trace_ev(trace, MR_GELU, ME_ACC2_READY, t);
             ptx::tc_fence_after();
 #pragma unroll 1
             for (int c0 = slice * 32; c0 < C; c0 += 128) {       // 32-column chunks, interleaved over the four warps of a lane quarter
@@ -282,6 +305,7 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(l_acc2_empty);
+            if (ew == 0 && lane == 0) trace_ev(trace, MR_GELU, ME_TILE_DONE, t);
             ++tiles_done;
         }
     }
@@ -318,8 +342,10 @@ int launch_mlp(const __half* a16, int64_t M, const __half* w1, const float* b1, 
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    PB_CUDA(cudaLaunchKernelEx(&cfg, vq_mlp_fused_kernel<C>, ta, tw1, tw2a, tw2b, b1, b2, x, alpha, (int)M));
+    const TraceBuf trace = C == 384 ? trace_begin("vq_mlp") : TraceBuf{nullptr};
+    PB_CUDA(cudaLaunchKernelEx(&cfg, vq_mlp_fused_kernel<C>, ta, tw1, tw2a, tw2b, b1, b2, x, alpha, (int)M, trace));
     PB_LAUNCH_CHECK();
+    if (trace.buf) PB_TRY(trace_end("vq_mlp", trace, kMlpRoles, kMlpEvents));
     return 0;
 }
 

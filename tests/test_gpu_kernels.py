@@ -294,7 +294,7 @@ def test_gemm_a_scale_equals_gemm_on_prescaled_a(M, N, K, P):
 
 
 def test_grn_fold_matches_separate_grn_pass():
-    """Model level: GRN folded into GEMM2 (default) vs the separate in-place GRN pass (PB200_NO_GRN_FOLD=1, child process):
+    """Model level: GRN folded into GEMM2 (opt-in PB200_GRN_FOLD=1, child process) vs the separate in-place GRN pass (default):
     features of the reference-default denoiser agree to fp16-rounding noise (the fold rounds h*s once, the pass rounds
     h*s + beta once and adds beta through the fp32 bias instead)."""
     import subprocess, sys
@@ -314,7 +314,7 @@ torch.save(f.cpu(), sys.argv[1])
     import tempfile
     outs = []
     with tempfile.TemporaryDirectory() as d:
-        for i, env in enumerate(({}, {"PB200_NO_GRN_FOLD": "1"})):
+        for i, env in enumerate(({"PB200_GRN_FOLD": "1"}, {})):
             path = os.path.join(d, f"f{i}.pt")
             r = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, env=dict(os.environ, **env))
             assert r.returncode == 0, r.stderr[-3000:]

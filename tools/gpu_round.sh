@@ -13,7 +13,7 @@ tail -15 gpurun_out/${TAG}_pytest_attention.log
 timeout 600 python -m pytest tests/test_gpu_kernels.py -k "a_scale" -q --no-header -rf -p no:cacheprovider > gpurun_out/${TAG}_pytest_ascale.log 2>&1
 if [ $? -ne 0 ]; then
   echo "a_scale GEMM tests FAILED: rest of the round runs with PB200_NO_GRN_FOLD=1" | tee gpurun_out/${TAG}_grnfold_fallback.txt
-  export PB200_NO_GRN_FOLD=1
+  export PB200_GRN_FOLD_BROKEN=1
 fi
 tail -8 gpurun_out/${TAG}_pytest_ascale.log
 timeout 600 python -m pytest tests/test_gpu_parity_r2.py -k "vqgan_resblock" -q --no-header -rf -p no:cacheprovider > gpurun_out/${TAG}_pytest_vqmlp.log 2>&1

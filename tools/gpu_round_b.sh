@@ -6,7 +6,7 @@ O=gpurun_out
 mkdir -p $O
 for f in attention grnfold vqmlp; do
   if ls $O/*_${f}_fallback.txt > /dev/null 2>&1; then
-    case $f in attention) export PB200_ATTN_LEGACY=1;; grnfold) export PB200_NO_GRN_FOLD=1;; vqmlp) export PB200_VQ_MLP_UNFUSED=1;; esac
+    case $f in attention) export PB200_ATTN_LEGACY=1;; grnfold) export PB200_GRN_FOLD_BROKEN=1;; vqmlp) export PB200_VQ_MLP_UNFUSED=1;; esac
     echo "round B runs with the $f fallback"
   fi
 done
