@@ -314,6 +314,12 @@ int pb200_vqgan_resblock(float* x_nhwc, int batch, int h, int w, int c, const fl
                          const void* w1_f16, const float* b1, const void* w2_f16, const float* b2, const float* gammas_host,
                          void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Experiment kept for the record (measured slower than the two GEMMs, see csrc/vq_mlp.cu): the ResBlock MLP in one tcgen05
+ * kernel, x[rows, c] += alpha * (GELU(a16 W1^T + b1) W2^T + b2) with the 4c-wide hidden kept in TMEM / shared memory.
+ * c in {384, 192}, rows >= 256.  The codec uses it only with PB200_VQ_MLP_FUSED=1. */
+int pb200_vq_mlp_fused(const void* a16, int64_t rows, int c, const void* w1_f16, const float* b1, const void* w2_f16,
+                       const float* b2, float* x, float alpha, void* stream);
+
 /* Output forms of the decoder's last kernel (out_block: 1x1 conv + PixelShuffle, ref/src/vqgan.py:86-89), fused with what
  * the reference's callers do next (ref/src_distributed/train.py:168-171 `decode_indices(x).clamp(0, 1)`, then
  * torchvision.utils.save_image's `mul(255).add_(0.5).clamp_(0, 255).to(uint8)` on an HWC view):

@@ -114,6 +114,7 @@ SIGNATURES = {
     "pb200_vqgan_decode_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int64,
                                       c_void_p]),
     "pb200_vqgan_sync_params": (c_int, [c_void_p, c_void_p]),
+    "pb200_vq_mlp_fused": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
     "pb200_vqgan_resblock_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "pb200_vqgan_resblock": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, POINTER(c_float), c_void_p, c_int64, c_void_p]),

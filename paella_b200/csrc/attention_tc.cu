@@ -15,13 +15,17 @@
 // tcgen05.mma instructions (same accumulator along K for Q/K, adjacent accumulator columns along N for V).
 // An M=64 accumulator occupies 16 lanes of each of the four TMEM sub-partitions (row r -> lane 32*(r/16) + r%16; CUTLASS
 // cute/atom/mma_traits_sm100.hpp tmem_frg, M_MMA == 64), so each softmax / epilogue warp owns 16 query rows.
-// Warp roles (512 threads): 0 TMA producer, 1 MMA issuer + TMEM allocator, 2-3 loaders of the 16-wide operand tails, 4-7 and
-// 8-11 two softmax groups taking alternate query tiles (one group when S / P are single-buffered), 12-15 epilogue (a warp may
-// only touch the TMEM lanes of sub-partition warp_id % 4).  Pipelines (mbarriers): Q ring (2), K/V ring (2, or 1 when the tile
+// Warp roles (512 threads): 0 TMA producer of K and Q, 1 MMA issuer + TMEM allocator, 2 TMA producer of V, 4-7 and 8-11 two
+// softmax groups taking alternate query tiles (one group when S / P are single-buffered), 12-15 epilogue (a warp may only
+// touch the TMEM lanes of sub-partition warp_id % 4).  Pipelines (mbarriers): Q ring (2), K/V ring (2, or 1 when the tile
 // is large), S accumulators (2 if 2*keys + 80 <= 512 TMEM columns), P buffers (2 if shared memory allows), one O accumulator.
-// The 16-wide tails (20 % of the bytes) would be half of all TMA row requests as 32-byte boxes -- TMA issues one request per
-// box row, and round 2's first version spent ~9 600 cycles per (sample, head) unit on 1 800 of them -- so warps 2-3 bring the
-// tails in with 16-byte cp.async into the same 32B-swizzle layout and arrive on the same mbarrier (cp.async.mbarrier.arrive).
+// K and V of a unit are separate pipeline stages with their own producers (warp 0: K + Q, warp 2: V): the K tile is released as
+// soon as the unit's last S = Q K^T has been computed, the V tile after its last P V -- measured with the in-kernel timeline
+// (PB200_TRACE, profiles/r02_attention_timeline.md): with one K/V stage pair released after P V, the next-but-one unit's loads
+// (4 200-5 400 cycles for 66 KB in 1 800 TMA box rows) could not start before the whole softmax of the unit two back had finished.
+// Tried and dropped (same timeline): the 16-wide tails / all operands by cp.async from two loader warps instead of TMA
+// (31.6 / 49.3 ms per bench step against 26.8 ms all-TMA: 64 threads x 65 address computations per unit are slower than
+// the TMA's box rows).
 #include "attention.cuh"
 #include "gemm.cuh"
 
@@ -31,7 +35,6 @@ namespace {
 constexpr int TC_HD = 80;
 constexpr int TC_QT = 64;
 constexpr int TC_THREADS = 512;
-constexpr int TC_TAIL_THREADS = 64;
 constexpr int TC_O_COLS = 80;
 
 struct TcParams {
@@ -41,10 +44,6 @@ struct TcParams {
     int sbox;          // rows of one conditioning TMA box
     int n1;            // S columns = MMA1 N = self_rows + sbox (multiple of 16)
     int nkv, nsb, npb; // ring depths: K/V stages, S accumulators, P buffers
-    int tails_cp;      // 16-wide tails by cp.async (warps 2-3) instead of 32-byte TMA boxes
-    const __half* qkv; // raw pointers for the cp.async tail loads
-    const __half* ckv;
-    int c_rows;        // rows of the conditioning tensor (slots * S_max)
     const int* kv_len;
     const int* kv_slot;
     float scale_log2;
@@ -64,15 +63,15 @@ struct TcParams {
 enum { TR_TMA = 0, TR_TAIL = 1, TR_MMA = 2, TR_SM0 = 3, TR_SM1 = 4, TR_EPI = 5 };
 enum { TE_KV_ISSUE = 0, TE_Q_ISSUE, TE_KV_READY, TE_S_ISSUED, TE_P_READY, TE_O_ISSUED, TE_S_READY, TE_MAX_DONE, TE_P_FREE, TE_P_WRITTEN,
        TE_O_READY, TE_O_DONE, TE_TAIL_KV_ISSUED, TE_TAIL_Q_ISSUED, TE_UNIT_END };
-const char* const kTraceRoles[TRACE_ROLES] = {"tma", "tail", "mma", "softmax0", "softmax1", "epilogue", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-"};
+const char* const kTraceRoles[TRACE_ROLES] = {"tma_kq", "tma_v", "mma", "softmax0", "softmax1", "epilogue", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-"};
 const char* const kTraceEvents[] = {"kv_issue", "q_issue", "kv_ready", "s_issued", "p_ready", "o_issued", "s_ready", "max_done", "p_free",
-                                    "p_written", "o_ready", "o_done", "tail_kv_issued", "tail_q_issued", "unit_end"};
+                                    "p_written", "o_ready", "o_done", "v_issue", "unused", "unit_end"};
 
 constexpr uint32_t Q_BYTES = TC_QT * 160;      // one query tile: 64 x (128 + 32) bytes
 
 // barrier slots (8 bytes each)
-enum { BAR_QF = 0, BAR_QE = 2, BAR_KVF = 4, BAR_KVE = 6, BAR_SF = 8, BAR_SE = 10, BAR_PF = 12, BAR_PE = 14, BAR_OF = 16, BAR_OE = 17,
-       BAR_COUNT = 18 };
+enum { BAR_QF = 0, BAR_QE = 2, BAR_KF = 4, BAR_KE = 6, BAR_VF = 8, BAR_VE = 10, BAR_SF = 12, BAR_SE = 14, BAR_PF = 16, BAR_PE = 18,
+       BAR_OF = 20, BAR_OE = 21, BAR_COUNT = 22 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
@@ -98,10 +97,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
     }
     if (warp == 1) {
         if (lane == 0) {
-            const uint32_t ld_cnt = 1u + (p.tails_cp ? TC_TAIL_THREADS : 0u);      // TMA thread (+ the tail loaders' cp.async arrivals)
             for (int i = 0; i < 2; ++i) {
-                ptx::mbar_init(bar(BAR_QF + i), ld_cnt);  ptx::mbar_init(bar(BAR_QE + i), 1);
-                ptx::mbar_init(bar(BAR_KVF + i), ld_cnt); ptx::mbar_init(bar(BAR_KVE + i), 1);
+                ptx::mbar_init(bar(BAR_QF + i), 1); ptx::mbar_init(bar(BAR_QE + i), 1);
+                ptx::mbar_init(bar(BAR_KF + i), 1); ptx::mbar_init(bar(BAR_KE + i), 1);
+                ptx::mbar_init(bar(BAR_VF + i), 1); ptx::mbar_init(bar(BAR_VE + i), 1);
                 ptx::mbar_init(bar(BAR_SF + i), 1);  ptx::mbar_init(bar(BAR_SE + i), 4);
                 ptx::mbar_init(bar(BAR_PF + i), 4);  ptx::mbar_init(bar(BAR_PE + i), 1);
             }
@@ -125,97 +124,55 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
     auto kv_stage = [&](int st) { return smem_base + p.off_kv + (uint32_t)st * p.kv_bytes; };
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer: K tiles (per unit) and Q tiles (per query tile) =====================
         if (lane == 0) {
             int it = 0, uc = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
                 const int b = u / p.nhead, h = u - b * p.nhead;
                 const int slot = p.kv_slot ? p.kv_slot[b] : b;
                 const int st = uc % p.nkv;
-                ptx::mbar_wait(bar(BAR_KVE + st), (((uint32_t)(uc / p.nkv)) & 1u) ^ 1u);
-                const uint32_t fb = bar(BAR_KVF + st);
+                ptx::mbar_wait(bar(BAR_KE + st), (((uint32_t)(uc / p.nkv)) & 1u) ^ 1u);
+                const uint32_t fb = bar(BAR_KF + st);
                 trace_ev(p.trace, TR_TMA, TE_KV_ISSUE, uc);
-                ptx::mbar_arrive_expect_tx(fb, p.tails_cp == 2 ? 0u : 2u * (uint32_t)(p.self_rows + p.sbox) * (p.tails_cp ? 128u : 160u));
-                const uint32_t k64 = kv_stage(st), v64 = k64 + p.k64_bytes, k16 = v64 + p.k64_bytes, v16 = k16 + p.k16_bytes;
+                ptx::mbar_arrive_expect_tx(fb, (uint32_t)(p.self_rows + p.sbox) * 160u);
+                const uint32_t k64 = kv_stage(st), k16 = k64 + 2 * p.k64_bytes;
                 const int hc = h * TC_HD;
-                if (p.self_rows && p.tails_cp != 2) {
-                    const int row0 = b * p.P;
-                    ptx::tma_load_2d(&tm_s64, fb, k64, p.E + hc, row0);
-                    ptx::tma_load_2d(&tm_s64, fb, v64, 2 * p.E + hc, row0);
-                    if (!p.tails_cp) {
-                        ptx::tma_load_2d(&tm_s16, fb, k16, p.E + hc + 64, row0);
-                        ptx::tma_load_2d(&tm_s16, fb, v16, 2 * p.E + hc + 64, row0);
-                    }
+                if (p.self_rows) {
+                    ptx::tma_load_2d(&tm_s64, fb, k64, p.E + hc, b * p.P);
+                    ptx::tma_load_2d(&tm_s16, fb, k16, p.E + hc + 64, b * p.P);
                 }
-                const int crow = slot * p.S_max;
-                if (p.tails_cp != 2) {
-                    ptx::tma_load_2d(&tm_c64, fb, k64 + (uint32_t)p.self_rows * 128u, hc, crow);
-                    ptx::tma_load_2d(&tm_c64, fb, v64 + (uint32_t)p.self_rows * 128u, p.E + hc, crow);
-                }
-                if (!p.tails_cp) {
-                    ptx::tma_load_2d(&tm_c16, fb, k16 + (uint32_t)p.self_rows * 32u, hc + 64, crow);
-                    ptx::tma_load_2d(&tm_c16, fb, v16 + (uint32_t)p.self_rows * 32u, p.E + hc + 64, crow);
-                }
+                ptx::tma_load_2d(&tm_c64, fb, k64 + (uint32_t)p.self_rows * 128u, hc, slot * p.S_max);
+                ptx::tma_load_2d(&tm_c16, fb, k16 + (uint32_t)p.self_rows * 32u, hc + 64, slot * p.S_max);
                 for (int qt = 0; qt < p.n_qt; ++qt, ++it) {
                     const int qs = it & 1;
                     ptx::mbar_wait(bar(BAR_QE + qs), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
                     trace_ev(p.trace, TR_TMA, TE_Q_ISSUE, it);
-                    ptx::mbar_arrive_expect_tx(bar(BAR_QF + qs), p.tails_cp == 2 ? 0u : (p.tails_cp ? TC_QT * 128u : Q_BYTES));
-                    if (p.tails_cp != 2) ptx::tma_load_2d(&tm_q64, bar(BAR_QF + qs), q64(qs), hc, b * p.P + qt * TC_QT);
-                    if (!p.tails_cp) ptx::tma_load_2d(&tm_q16, bar(BAR_QF + qs), q16(qs), hc + 64, b * p.P + qt * TC_QT);
+                    ptx::mbar_arrive_expect_tx(bar(BAR_QF + qs), Q_BYTES);
+                    ptx::tma_load_2d(&tm_q64, bar(BAR_QF + qs), q64(qs), hc, b * p.P + qt * TC_QT);
+                    ptx::tma_load_2d(&tm_q16, bar(BAR_QF + qs), q16(qs), hc + 64, b * p.P + qt * TC_QT);
                 }
             }
         }
-    } else if (warp == 2 || warp == 3) {
-        // ===================== tail loaders: the 16-wide K / V / Q slices by cp.async, 32B-swizzle layout =====================
-        if (p.tails_cp) {
-            const int t = (warp - 2) * 32 + lane;
-            // tile row r, 16-byte chunk c (0/1) of a [rows x 32 B] SWIZZLE_32B tile lives at r*32 + ((c ^ ((r >> 2) & 1)) << 4)
-            auto dst = [](uint32_t tile, int r, int c) { return tile + (uint32_t)(r * 32 + ((c ^ ((r >> 2) & 1)) << 4)); };
-            const int64_t ldq = 3 * (int64_t)p.E, ldc = 2 * (int64_t)p.E;
-            const int q_rows = p.B * p.P;
-            int it = 0, uc = 0;
+    } else if (warp == 2) {
+        // ===================== TMA producer: V tiles (their stage frees much later than K's: own thread, own barriers) =====================
+        if (lane == 0) {
+            int uc = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
                 const int b = u / p.nhead, h = u - b * p.nhead;
                 const int slot = p.kv_slot ? p.kv_slot[b] : b;
                 const int st = uc % p.nkv;
-                ptx::mbar_wait(bar(BAR_KVE + st), (((uint32_t)(uc / p.nkv)) & 1u) ^ 1u);
-                const uint32_t k64 = kv_stage(st), v64 = k64 + p.k64_bytes, k16 = v64 + p.k64_bytes, v16 = k16 + p.k16_bytes;
-                const int col0 = h * TC_HD;
-                const int n_rows = p.self_rows + p.sbox;
-                // chunk c of a row: c < 8 -> the 64-wide tile (128B swizzle: chunk ^ (row & 7)), c = 8, 9 -> the 16-wide tail
-                const int c_lo = p.tails_cp == 2 ? 0 : 8, per_row = 10 - c_lo;
-                for (int i = t; i < n_rows * per_row; i += TC_TAIL_THREADS) {
-                    const int r = i / per_row, c = c_lo + (i - r * per_row);
-                    const __half* ks;
-                    bool ok = true;
-                    if (r < p.self_rows) {
-                        ks = p.qkv + ((int64_t)b * p.P + r) * ldq + p.E + col0 + c * 8;
-                    } else {
-                        const int64_t cr = (int64_t)slot * p.S_max + (r - p.self_rows);
-                        ok = cr < p.c_rows;
-                        ks = p.ckv + (ok ? cr : 0) * ldc + col0 + c * 8;
-                    }
-                    const uint32_t dk = c < 8 ? k64 + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)) : dst(k16, r, c - 8);
-                    const uint32_t dv = c < 8 ? v64 + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)) : dst(v16, r, c - 8);
-                    ptx::cp_async16(dk, ks, ok);
-                    ptx::cp_async16(dv, ks + p.E, ok);          // v sits E columns after k in both tensors
+                ptx::mbar_wait(bar(BAR_VE + st), (((uint32_t)(uc / p.nkv)) & 1u) ^ 1u);
+                const uint32_t fb = bar(BAR_VF + st);
+                trace_ev(p.trace, TR_TAIL, TE_TAIL_KV_ISSUED, uc);
+                ptx::mbar_arrive_expect_tx(fb, (uint32_t)(p.self_rows + p.sbox) * 160u);
+                const uint32_t v64 = kv_stage(st) + p.k64_bytes, v16 = v64 + p.k64_bytes + p.k16_bytes;
+                const int hc = h * TC_HD;
+                if (p.self_rows) {
+                    ptx::tma_load_2d(&tm_s64, fb, v64, 2 * p.E + hc, b * p.P);
+                    ptx::tma_load_2d(&tm_s16, fb, v16, 2 * p.E + hc + 64, b * p.P);
                 }
-                ptx::cp_async_mbar_arrive_noinc(bar(BAR_KVF + st));
-                if (t == 0) trace_ev(p.trace, TR_TAIL, TE_TAIL_KV_ISSUED, uc);
-                for (int qt = 0; qt < p.n_qt; ++qt, ++it) {
-                    const int qs = it & 1;
-                    ptx::mbar_wait(bar(BAR_QE + qs), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
-                    for (int i = t; i < TC_QT * per_row; i += TC_TAIL_THREADS) {
-                        const int r = i / per_row, c = c_lo + (i - r * per_row);
-                        const int64_t gr = (int64_t)b * p.P + qt * TC_QT + r;
-                        const bool ok = gr < q_rows;
-                        const uint32_t dq = c < 8 ? q64(qs) + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)) : dst(q16(qs), r, c - 8);
-                        ptx::cp_async16(dq, p.qkv + (ok ? gr : 0) * ldq + col0 + c * 8, ok);
-                    }
-                    ptx::cp_async_mbar_arrive_noinc(bar(BAR_QF + qs));
-                    if (t == 0) trace_ev(p.trace, TR_TAIL, TE_TAIL_Q_ISSUED, it);
-                }
+                ptx::tma_load_2d(&tm_c64, fb, v64 + (uint32_t)p.self_rows * 128u, p.E + hc, slot * p.S_max);
+                ptx::tma_load_2d(&tm_c16, fb, v16 + (uint32_t)p.self_rows * 32u, p.E + hc + 64, slot * p.S_max);
             }
         }
     } else if (warp == 1) {
@@ -237,13 +194,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
         auto issue_s = [&](const Cur& c) {
             const int st = c.uc % p.nkv;
             if (c.qt == 0) {
-                ptx::mbar_wait(bar(BAR_KVF + st), ((uint32_t)(c.uc / p.nkv)) & 1u);
+                ptx::mbar_wait(bar(BAR_KF + st), ((uint32_t)(c.uc / p.nkv)) & 1u);
                 if (lane == 0) trace_ev(p.trace, TR_MMA, TE_KV_READY, c.uc);
             }
             const int qs = c.it & 1, sb = c.it % p.nsb;
             ptx::mbar_wait(bar(BAR_QF + qs), ((uint32_t)(c.it >> 1)) & 1u);
             ptx::mbar_wait(bar(BAR_SE + sb), (((uint32_t)(c.it / p.nsb)) & 1u) ^ 1u);
-            if (p.tails_cp) ptx::fence_proxy_async_smem();      // cp.async data arrived through the generic proxy
             ptx::tc_fence_after();
             if (lane == 0) {
                 const uint32_t k64 = kv_stage(st), k16 = k64 + 2 * p.k64_bytes;
@@ -260,6 +216,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 }
                 ptx::umma_commit(bar(BAR_SF + sb));
                 ptx::umma_commit(bar(BAR_QE + qs));
+                if (c.qt == p.n_qt - 1) ptx::umma_commit(bar(BAR_KE + st));         // the unit's K tile is free for the next-but-one unit
                 trace_ev(p.trace, TR_MMA, TE_S_ISSUED, c.it);
             }
             __syncwarp();
@@ -271,6 +228,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
             const int slot = p.kv_slot ? p.kv_slot[b] : b;
             const int nk = p.self_rows + (p.kv_len ? p.kv_len[slot] : p.S_max);
             const int nks = (nk + 15) >> 4;
+            if (c.qt == 0) ptx::mbar_wait(bar(BAR_VF + st), ((uint32_t)(c.uc / p.nkv)) & 1u);
             ptx::mbar_wait(bar(BAR_PF + pb), ((uint32_t)(c.it / p.npb)) & 1u);
             if (lane == 0) trace_ev(p.trace, TR_MMA, TE_P_READY, c.it);
             ptx::mbar_wait(bar(BAR_OE), (((uint32_t)c.it) & 1u) ^ 1u);
@@ -286,7 +244,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 }
                 ptx::umma_commit(bar(BAR_OF));
                 ptx::umma_commit(bar(BAR_PE + pb));
-                if (c.qt == p.n_qt - 1) ptx::umma_commit(bar(BAR_KVE + st));
+                if (c.qt == p.n_qt - 1) ptx::umma_commit(bar(BAR_VE + st));
                 trace_ev(p.trace, TR_MMA, TE_O_ISSUED, c.it);
             }
             __syncwarp();
@@ -295,7 +253,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
         if (valid(c)) issue_s(c);
         while (valid(c)) {
             const Cur n = next(c);
-            // S of the next tile overlaps this tile's softmax when it has its own accumulator and (across units) its own K/V stage
+            // S of the next tile overlaps this tile's softmax when it has its own accumulator and (across units) its own K stage
             const bool ahead = valid(n) && p.nsb == 2 && (n.uc == c.uc || p.nkv == 2);
             if (ahead) issue_s(n);
             issue_o(c);
@@ -309,8 +267,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
         const int group = (warp - 4) >> 2;
         const int n_groups = (p.nsb == 2 && p.npb == 2) ? 2 : 1;
         const int wq = warp & 3;
-        const int row = wq * 16 + lane;                 // query row of this thread inside the tile (lanes 16..31 carry none)
-        const bool lane_ok = lane < 16;
+        // tcgen05.ld 16x256b: thread t holds rows t/4 and t/4 + 8 of this warp's 16, columns 8n + 2(t%4) + {0,1} of every 64-column
+        // piece -- all 32 lanes carry scores (the 32x32b shape, one row per lane, leaves half the warp idle on an M = 64 tile)
+        const int qd = lane & 3;
+        const int row0 = wq * 16 + (lane >> 2), row1 = row0 + 8;          // this thread's two query rows inside the tile
         int it = 0;
         if (group < n_groups)
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -329,58 +289,64 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 if (tr) trace_ev(p.trace, TR_SM0 + group, TE_S_READY, it);
                 ptx::tc_fence_after();
                 const uint32_t ts = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(sb * p.n1);
-                float m = -INFINITY;
+                float m0 = -INFINITY, m1 = -INFINITY;
                 if (rows_here) {
                     for (int c0 = 0; c0 < nk; c0 += 64) {
-                        float v[64];
-                        ptx::tmem_ld_32x64(ts + (uint32_t)c0, v);
-                        if (c0 + 64 <= nk) {
+                        float v[32];
+                        ptx::tmem_ld_16x256b_x8(ts + (uint32_t)c0, v);
+                        const bool full = c0 + 64 <= nk;
 #pragma unroll
-                            for (int j = 0; j < 64; ++j) m = fmaxf(m, v[j]);
-                        } else {
+                        for (int n = 0; n < 8; ++n)
 #pragma unroll
-                            for (int j = 0; j < 64; ++j) m = (c0 + j < nk) ? fmaxf(m, v[j]) : m;
-                        }
+                            for (int e = 0; e < 2; ++e) {
+                                const bool ok = full || c0 + 8 * n + 2 * qd + e < nk;
+                                m0 = ok ? fmaxf(m0, v[4 * n + e]) : m0;
+                                m1 = ok ? fmaxf(m1, v[4 * n + 2 + e]) : m1;
+                            }
                     }
+                    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+                    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
                 }
                 if (tr) trace_ev(p.trace, TR_SM0 + group, TE_MAX_DONE, it);
                 ptx::mbar_wait(bar(BAR_PE + pb), (((uint32_t)(it / p.npb)) & 1u) ^ 1u);     // the P buffer is free again
                 if (tr) trace_ev(p.trace, TR_SM0 + group, TE_P_FREE, it);
-                float l = 0.f;
+                float l0 = 0.f, l1 = 0.f;
                 if (rows_here) {
-                    const float msc = m * p.scale_log2;
-                    uint8_t* prow = smem_gen + p.off_p + (size_t)pb * p.p_bytes + (size_t)row * 128;
+                    const float ms0 = m0 * p.scale_log2, ms1 = m1 * p.scale_log2;
+                    uint8_t* pt = smem_gen + p.off_p + (size_t)pb * p.p_bytes;
                     for (int c0 = 0; c0 < nk16; c0 += 64) {      // one 64-key atom of the P tile per iteration
-                        float v[64];
-                        ptx::tmem_ld_32x64(ts + (uint32_t)c0, v);
+                        float v[32];
+                        ptx::tmem_ld_16x256b_x8(ts + (uint32_t)c0, v);
                         const bool full = c0 + 64 <= nk;
+                        uint8_t* atom = pt + (size_t)(c0 >> 6) * 8192;
 #pragma unroll
-                        for (int j = 0; j < 64; ++j) {
-                            const float e = ptx::ex2_approx(fmaf(v[j], p.scale_log2, -msc));
-                            v[j] = (full || c0 + j < nk) ? e : 0.f;
-                            l += v[j];
-                        }
-                        if (weighted) {
-#pragma unroll
-                            for (int j = 0; j < 64; ++j) {
-                                const int kj = c0 + j;
-                                if (kj >= w_start && kj < nk) v[j] *= p.attn_w[kj - w_start];
+                        for (int n = 0; n < 8; ++n) {
+                            float e00 = ptx::ex2_approx(fmaf(v[4 * n + 0], p.scale_log2, -ms0)), e01 = ptx::ex2_approx(fmaf(v[4 * n + 1], p.scale_log2, -ms0));
+                            float e10 = ptx::ex2_approx(fmaf(v[4 * n + 2], p.scale_log2, -ms1)), e11 = ptx::ex2_approx(fmaf(v[4 * n + 3], p.scale_log2, -ms1));
+                            const int kj = c0 + 8 * n + 2 * qd;
+                            if (!full) {
+                                if (kj >= nk) { e00 = 0.f; e10 = 0.f; }
+                                if (kj + 1 >= nk) { e01 = 0.f; e11 = 0.f; }
                             }
-                        }
-                        if (lane_ok) {
-                            uint8_t* atom = prow + (size_t)(c0 >> 6) * 8192;
-#pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                uint4 pk;
-                                pk.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
-                                pk.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
-                                *reinterpret_cast<uint4*>(atom + ((g ^ (row & 7)) << 4)) = pk;
+                            l0 += e00 + e01;
+                            l1 += e10 + e11;
+                            if (weighted) {
+                                if (kj >= w_start && kj < nk) { const float ww = p.attn_w[kj - w_start]; e00 *= ww; e10 *= ww; }
+                                if (kj + 1 >= w_start && kj + 1 < nk) { const float ww = p.attn_w[kj + 1 - w_start]; e01 *= ww; e11 *= ww; }
                             }
+                            // keys kj, kj+1 = 4 bytes of 16-byte chunk n of the row (K-major 128B swizzle: chunk ^ (row & 7))
+                            *reinterpret_cast<uint32_t*>(atom + row0 * 128 + ((n ^ (row0 & 7)) << 4) + qd * 4) = pack_half2(e00, e01);
+                            *reinterpret_cast<uint32_t*>(atom + row1 * 128 + ((n ^ (row1 & 7)) << 4) + qd * 4) = pack_half2(e10, e11);
                         }
                     }
+                    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+                    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
                 }
                 ptx::tc_fence_before();
-                if (lane_ok) invl[(it & 3) * TC_QT + row] = 1.0f / l;
+                if (qd == 0) {
+                    invl[(it & 3) * TC_QT + row0] = 1.0f / l0;
+                    invl[(it & 3) * TC_QT + row1] = 1.0f / l1;
+                }
                 ptx::fence_proxy_async_smem();          // P (generic-proxy stores) must be visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) {
@@ -468,12 +434,6 @@ int launch_attention_tc(const AttnParams& a, cudaStream_t st) {
     p.n1 = (p.self_rows + a.S_max + 15) & ~15;
     p.sbox = p.n1 - p.self_rows;
     if (p.sbox > 256 || p.n1 + TC_O_COLS > 512 || (p.n1 > 256 && p.n1 - 256 < 16)) return -1;
-    // A/B knobs: PB200_ATTN_TAILS_TMA=1: everything by TMA (32-byte boxes for the tails); PB200_ATTN_ALL_CP=1: everything by cp.async
-    static const bool tails_tma = getenv("PB200_ATTN_TAILS_TMA") != nullptr;
-    static const bool all_cp = getenv("PB200_ATTN_ALL_CP") != nullptr;
-    p.tails_cp = tails_tma ? 0 : (all_cp ? 2 : 1);
-    p.qkv = a.qkv; p.ckv = a.ckv;
-    p.c_rows = (a.n_slots > 0 ? a.n_slots : a.B) * a.S_max;
     p.kv_len = a.kv_len; p.kv_slot = a.kv_slot; p.scale_log2 = a.scale_log2;
     p.attn_w = a.attn_w; p.n_w = a.attn_w ? a.n_w : 0; p.w_batch = a.w_batch; p.out = a.out;
     p.k64_bytes = (uint32_t)p.n1 * 128u;

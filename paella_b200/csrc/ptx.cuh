@@ -227,6 +227,26 @@ __device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, float (&v)[64]) {
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 lanes x 64 consecutive fp32 columns in the mma C-fragment arrangement (cute SM100_TMEM_LOAD_16dp256b8x): thread t holds
+// lane t/4 (registers 4n, 4n+1) and lane t/4 + 8 (registers 4n+2, 4n+3), columns 8n + 2(t%4) + {0, 1}, n = 0..7 -- all 32
+// threads carry data of a 16-lane (M = 64) accumulator slice, where the 32x32b shape leaves lanes 16..31 idle
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // 16-byte cp.async (zero-fill when !valid) and the mbarrier arrival that fires when this thread's earlier cp.asyncs have landed
 // (.noinc: a plain arrival, to be counted in the barrier's init count)
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, bool valid) {

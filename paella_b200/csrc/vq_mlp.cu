@@ -1,3 +1,10 @@
+// MEASURED SLOWER THAN THE TWO GEMMS IT REPLACES -- opt-in (PB200_VQ_MLP_FUSED=1), kept with its tests as a recorded experiment:
+// 17.2 vs 12.7 ms per 64-image round trip (B200, profiles/r02_vqmlp_timeline.md).  The in-kernel timeline shows why: a 64-wide
+// hidden chunk makes GEMM1 re-read the whole 128 x C A tile from shared memory for only 64 output columns (24 x 96 KB per tile;
+// a plain GEMM tile amortises its A reads over 256 columns), so one chunk moves ~270 KB through the 128 B/clk shared-memory port
+// (>= 2 100 cycles) for 1 536 cycles of tensor work, and the N = 64 MMAs themselves issue at ~112 cycles instead of 32.  A wider
+// chunk does not fit TMEM next to the C-column output accumulator with double buffering.
+//
 // Fused MLP of the codec's ResBlock (ref/src/vqgan.py:16-20,40-41):
 //     x += alpha * ( GELU(a W1^T + b1) W2^T + b2 ),   a = fp16 [M, C] (LayerNorm'd rows), W1 [4C, C], W2 [C, 4C]
 // in ONE kernel: the 4C-wide hidden never leaves the SM.  The two-kernel form (GEMM1 -> fp16 hidden in HBM -> GEMM2) moves
@@ -354,8 +361,7 @@ int launch_mlp(const __half* a16, int64_t M, const __half* w1, const float* b1, 
 // x[M, C] += alpha * (GELU(a16 W1^T + b1) W2^T + b2).  0 = launched, 1 = error, -1 = shape not handled (caller runs two GEMMs)
 int launch_vq_mlp_fused(const __half* a16, int64_t M, int C, const __half* w1, const float* b1, const __half* w2, const float* b2,
                         float* x, float alpha, cudaStream_t st) {
-    static const bool off = getenv("PB200_VQ_MLP_UNFUSED") != nullptr;      // A/B knob
-    if (off || M < 256 || M >= (1ll << 31) || sm_count() % 2 != 0) return -1;
+    if (M < 256 || M >= (1ll << 31) || sm_count() % 2 != 0) return -1;
     ProfScope prof("gemm_vq_mlp_fused", 16.0 * (double)M * (double)C * (double)C, st);
     if (C == 384) return launch_mlp<384>(a16, M, w1, b1, w2, b2, x, alpha, st);
     if (C == 192) return launch_mlp<192>(a16, M, w1, b1, w2, b2, x, alpha, st);

@@ -346,7 +346,8 @@ static int run_resblock(pb200_vqgan* m, const VqResBlock& rb, float* x, int B, i
     const int c = rb.c;
     const int64_t M = (int64_t)B * h * w;
     PB_TRY(resblock_front(x, B, h, w, c, m->w<float>(rb.dw_w), m->w<float>(rb.dw_b), rb.gam, ws.tmp32, ws.a16, st));
-    {       // Linear -> GELU -> Linear -> x + g5 * (.) in one kernel, the 4c hidden never leaves the SM (vq_mlp.cu)
+    static const bool fused = getenv("PB200_VQ_MLP_FUSED") != nullptr;      // experiment knob: see vq_mlp.cu (measured slower)
+    if (fused) {    // Linear -> GELU -> Linear -> x + g5 * (.) in one kernel, the 4c hidden never leaves the SM
         const int rc = launch_vq_mlp_fused(ws.a16, M, c, m->w<__half>(rb.w1), m->w<float>(rb.b1), m->w<__half>(rb.w2), m->w<float>(rb.b2), x,
                                            rb.gam[5], st);
         if (rc >= 0) return rc;
@@ -391,16 +392,20 @@ int pb200_vqgan_resblock(float* x_nhwc, int batch, int h, int w, int c, const fl
     __half* a16 = reinterpret_cast<__half*>(base + up(M * c * 4));
     __half* h16 = reinterpret_cast<__half*>(base + up(M * c * 4) + up(M * c * 2));
     PB_TRY(resblock_front(x_nhwc, batch, h, w, c, dw_w9, dw_bias, gammas_host, tmp32, a16, st));
-    {
-        const int rc = launch_vq_mlp_fused(a16, M, c, reinterpret_cast<const __half*>(w1_f16), b1, reinterpret_cast<const __half*>(w2_f16), b2,
-                                           x_nhwc, gammas_host[5], st);
-        if (rc >= 0) return rc;
-    }
     pb200_gemm_epilogue e1 = vepi(PB200_EPI_GELU_F16, b1, h16, 4 * c);
     PB_TRY(gemm_f16(a16, c, w1_f16, c, M, 4 * (int64_t)c, c, e1, st));
     pb200_gemm_epilogue e2 = vepi(PB200_EPI_RESID_F32, b2, x_nhwc, c);
     e2.resid = x_nhwc; e2.ldr = c; e2.alpha = gammas_host[5];
     return gemm_f16(h16, 4 * (int64_t)c, w2_f16, 4 * (int64_t)c, M, c, 4 * (int64_t)c, e2, st);
+}
+
+int pb200_vq_mlp_fused(const void* a16, int64_t rows, int c, const void* w1_f16, const float* b1, const void* w2_f16, const float* b2,
+                       float* x, float alpha, void* stream) {
+    PB_CHECK(a16 && w1_f16 && b1 && w2_f16 && b2 && x, "vq_mlp_fused: null pointer");
+    const int rc = launch_vq_mlp_fused(reinterpret_cast<const __half*>(a16), rows, c, reinterpret_cast<const __half*>(w1_f16), b1,
+                                       reinterpret_cast<const __half*>(w2_f16), b2, x, alpha, (cudaStream_t)stream);
+    PB_CHECK(rc >= 0, "vq_mlp_fused: built for c in {384, 192} and rows >= 256 only (got c=%d, rows=%lld)", c, (long long)rows);
+    return rc;
 }
 
 int pb200_vqgan_create(const pb200_vqgan_config* cfg, pb200_vqgan** out) {

@@ -293,6 +293,33 @@ def test_gemm_a_scale_equals_gemm_on_prescaled_a(M, N, K, P):
     assert float((got - ref).abs().max()) < 2e-4
 
 
+@pytest.mark.parametrize("c,rows", [(384, 8192), (192, 4352), (384, 300)])
+def test_vq_mlp_fused_equals_two_gemms(c, rows):
+    """The fused codec MLP kernel (opt-in experiment, csrc/vq_mlp.cu) against the two GEMM launches it replaces: same fp16 GELU
+    hidden, same K order of the second contraction -> agreement to fp32 accumulation noise."""
+    from paella_b200 import _lib
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(31)
+    a = torch.randn(rows, c, device=DEV, generator=g).half()
+    w1 = (torch.randn(4 * c, c, device=DEV, generator=g) / math.sqrt(c)).half()
+    w2 = (torch.randn(c, 4 * c, device=DEV, generator=g) / math.sqrt(4 * c)).half()
+    b1 = torch.randn(4 * c, device=DEV, generator=g) * 0.1
+    b2 = torch.randn(c, device=DEV, generator=g) * 0.1
+    x0 = torch.randn(rows, c, device=DEV, generator=g)
+    alpha = 0.7
+    h = torch.empty(rows, 4 * c, device=DEV, dtype=torch.float16)
+    ops.gemm_f16(a, w1, _lib.EPI_GELU_F16, h, bias=b1)
+    want = x0.clone()
+    ops.gemm_f16(h, w2, _lib.EPI_RESID_F32, want, bias=b2, resid=want, alpha=alpha)
+    got = x0.clone()
+    _lib.check(_lib.lib().pb200_vq_mlp_fused(_lib.ptr(a), rows, c, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(got),
+                                            alpha, _lib.current_stream()), "pb200_vq_mlp_fused")
+    torch.cuda.synchronize()
+    err = float((got - want).abs().max())
+    _log("vq_mlp_fused", {"c": c, "rows": rows, "max_abs_vs_two_gemms": err})
+    assert err < 2e-5
+
+
 def test_grn_fold_matches_separate_grn_pass():
     """Model level: GRN folded into GEMM2 (opt-in PB200_GRN_FOLD=1, child process) vs the separate in-place GRN pass (default):
     features of the reference-default denoiser agree to fp16-rounding noise (the fold rounds h*s once, the pass rounds

@@ -176,7 +176,7 @@ def test_vq_indices_vs_torchtools_addmm_form_with_margin_audit():
     addmm(|c|^2 + |x|^2, x, c^T, alpha=-2) -> first minimum), not vs an oracle that copies the kernel's fma order.  The two
     evaluate the same real-valued distance with different fp32 roundings, so exact equality is not implied; every disagreement
     must be a tie within the rounding noise of the expanded form (a sum of ~6 fp32 roundings per entry, two entries):
-    |d_a - d_b| <= 16 ulp(|x|^2 + |c|^2)."""
+    |d_a - d_b| <= 4 ulp(|x|^2 + |c|^2) (measured on B200: 0.74 ulp worst, 6 mismatches in 350 000 vectors)."""
     from oracle import vqgan_oracle as vo
     from paella_b200 import ops
     g = torch.Generator().manual_seed(5)
@@ -202,7 +202,7 @@ def test_vq_indices_vs_torchtools_addmm_form_with_margin_audit():
             worst_ulps = float((gap / ulp).max())
         out[name] = {"n": x.shape[0], "mismatch": int(bad.numel()), "agree": 1 - bad.numel() / x.shape[0], "worst_gap_ulps": worst_ulps}
         assert out[name]["agree"] > 0.999, out
-        assert worst_ulps <= 16.0, out
+        assert worst_ulps <= 4.0, out
     _log("vq_vs_addmm", out)
 
 

@@ -16,12 +16,6 @@ if [ $? -ne 0 ]; then
   export PB200_GRN_FOLD_BROKEN=1
 fi
 tail -8 gpurun_out/${TAG}_pytest_ascale.log
-timeout 600 python -m pytest tests/test_gpu_parity_r2.py -k "vqgan_resblock" -q --no-header -rf -p no:cacheprovider > gpurun_out/${TAG}_pytest_vqmlp.log 2>&1
-if [ $? -ne 0 ]; then
-  echo "codec ResBlock tests FAILED with the fused MLP kernel: rest of the round runs with PB200_VQ_MLP_UNFUSED=1" | tee gpurun_out/${TAG}_vqmlp_fallback.txt
-  export PB200_VQ_MLP_UNFUSED=1
-fi
-tail -8 gpurun_out/${TAG}_pytest_vqmlp.log
 timeout 1500 python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider --deselect tests/test_gpu_attention.py > gpurun_out/${TAG}_pytest.log 2>&1
 tail -40 gpurun_out/${TAG}_pytest.log
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
