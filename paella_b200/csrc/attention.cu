@@ -246,7 +246,9 @@ int launch_attention(const AttnParams& p, cudaStream_t st) {
     PB_CHECK(p.E % 8 == 0, "attention: E must be a multiple of 8");
     if (p.B == 0 || p.P == 0) return 0;
     {
-        const int rc = launch_attention_tc(p, st);
+        int rc = launch_attention_tt(p, st);
+        if (rc >= 0) return rc;
+        rc = launch_attention_tc(p, st);
         if (rc >= 0) return rc;
     }
     // algorithmic bytes: q, self k/v, out once; conditioning k/v once per sample

@@ -23,5 +23,6 @@ struct AttnParams {
 // mma.sync kernel below for every other shape (tiny test configs, odd head dims, very long key lists).
 int launch_attention(const AttnParams& p, cudaStream_t st);
 int launch_attention_tc(const AttnParams& p, cudaStream_t st);      // 0 launched, 1 error, -1 shape not handled
+int launch_attention_tt(const AttnParams& p, cudaStream_t st);      // transposed (keys on M = 128) variant for <= 64 queries: same codes
 
 }  // namespace pb

@@ -434,6 +434,11 @@ int launch_attention_tc(const AttnParams& a, cudaStream_t st) {
     p.n1 = (p.self_rows + a.S_max + 15) & ~15;
     p.sbox = p.n1 - p.self_rows;
     if (p.sbox > 256 || p.n1 + TC_O_COLS > 512 || (p.n1 > 256 && p.n1 - 256 < 16)) return -1;
+    // more than 256 keys (64x64 latents, level 1): S needs two N-split instructions per k-step on an M = 64 tile and a single
+    // S accumulator -- measured slower than the mma.sync kernel (57.6 against 38.2 ms of attention per 12-step sample at bs 16,
+    // profiles/r02_ab_notes.md), so that shape is only taken on request (PB200_ATTN_TC_WIDE=1; tests keep it covered)
+    static const bool wide = getenv("PB200_ATTN_TC_WIDE") != nullptr;
+    if (p.n1 > 256 && !wide) return -1;
     p.kv_len = a.kv_len; p.kv_slot = a.kv_slot; p.scale_log2 = a.scale_log2;
     p.attn_w = a.attn_w; p.n_w = a.attn_w ? a.n_w : 0; p.w_batch = a.w_batch; p.out = a.out;
     p.k64_bytes = (uint32_t)p.n1 * 128u;

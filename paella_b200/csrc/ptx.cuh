@@ -247,6 +247,9 @@ __device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float (&v)[32
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// named barrier among `nthreads` threads (a subset of the CTA's warps)
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // 16-byte cp.async (zero-fill when !valid) and the mbarrier arrival that fires when this thread's earlier cp.asyncs have landed
 // (.noinc: a plain arrival, to be counted in the barrier's init count)
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, bool valid) {
@@ -288,6 +291,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_b
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)layout_type << 61;
+    return d;
+}
+// MN-major operand spanning several 64-element (128-byte) swizzle atoms along M/N: lbo_bytes = distance between the atoms' tiles
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = umma_desc(smem_addr, 1024, 2);
+    d &= ~((uint64_t)0x3FFF << 16);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     return d;
 }
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) { return umma_desc(smem_addr, 1024, 2); }

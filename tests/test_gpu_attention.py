@@ -80,7 +80,7 @@ def _run(B, P, S, H, hd, self_attn, varlen, weighted, seed=0):
 TC_CASES = [
     (4, 64, 132, 16, 80, True, False, False),      # BASELINE config 2, level 1: 196 keys, 2 S accumulators, 2 K/V stages
     (3, 16, 132, 16, 80, True, True, False),       # config 2, level 2: 16 queries in a 64-row tile
-    (2, 256, 136, 16, 80, True, True, False),      # config 4, level 1: 4 query tiles per unit, 392 keys (N split 256 + 144)
+    (2, 256, 136, 16, 80, True, True, False),      # config 4, level 1: 392 keys -> mma.sync by default, attention_tc with PB200_ATTN_TC_WIDE
     (2, 64, 136, 16, 80, True, False, True),       # config 4, level 2 + attn_weights
     (5, 64, 20, 4, 80, False, True, False),        # cross-attention only, short ragged conditioning
     (2, 128, 7, 2, 80, True, False, False),        # two query tiles, odd conditioning length
@@ -88,11 +88,37 @@ TC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", TC_CASES)
+# shapes of the transposed kernel (csrc/attention_tt.cu: <= 64 queries, <= 256 keys, no attn_weights) beyond those in TC_CASES
+TT_CASES = [
+    (6, 64, 100, 4, 80, True, True, False),        # ragged: some samples end inside key tile 0 (tile 1 fully masked), some in tile 1
+    (3, 32, 12, 2, 80, True, False, False),        # one key tile (48 keys), 32 queries in the 64-wide N
+    (2, 64, 190, 16, 80, True, True, False),       # 254 -> 256 keys: the largest tile set (single V stage)
+    (300, 64, 132, 16, 80, True, True, False),     # ring wrap-around with ragged lengths (33 units per CTA)
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES + TT_CASES)
 def test_tcgen05_attention_vs_fp32_reference(case):
+    """The default dispatch: attention_tt for <= 64 queries / <= 256 keys without attn_weights, attention_tc otherwise."""
     mx, rms, _ = _run(*case)
     _log({"kernel": "tcgen05", "case": case, "max_abs": mx, "rms": rms})
     assert mx < 4e-3 and rms < 4e-4, (case, mx, rms)      # outputs are O(1): fp16 P and fp16 output rounding
+
+
+def test_tcgen05_row_major_kernel_on_the_transposed_kernels_shapes():
+    """PB200_ATTN_NO_TT=1 (child process) sends every head_dim-80 shape to attention_tc.cu: it stays covered on the shapes the
+    transposed kernel normally takes."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    cases = [c for c in TC_CASES + TT_CASES if not c[7]]       # incl. the > 256-key shape (PB200_ATTN_TC_WIDE), mma.sync by default
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_attention as t\n"
+            "for c in %r:\n    mx, rms, _ = t._run(*c); print('RES', mx, rms)") % (os.path.dirname(here), here, cases)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PB200_ATTN_NO_TT="1", PB200_ATTN_TC_WIDE="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = [tuple(float(x) for x in l.split()[1:]) for l in r.stdout.splitlines() if l.startswith("RES")]
+    assert len(res) == len(cases)
+    for c, (mx, rms) in zip(cases, res):
+        _log({"kernel": "tcgen05-rowmajor", "case": c, "max_abs": mx, "rms": rms})
+        assert mx < 4e-3 and rms < 4e-4, (c, mx, rms)
 
 
 @pytest.mark.parametrize("case", [(2, 64, 9, 4, 16, True, False, False), (2, 16, 20, 4, 32, True, True, True),
