@@ -8,10 +8,14 @@
 //   softmax  down the TMEM LANES: thread = one key row, its 64 registers = the 64 queries.  Column max by an in-warp
 //            transpose-reduce (62 shuffles leave columns 2*lane, 2*lane+1 in each lane) + one shared-memory stage across the
 //            warps; P^T = exp2(..) (fp16) is written as one full 128-byte row per thread = the MN-major 128B-swizzle layout
-//   MMA2   O^T[128 x 64 q] = V^T P^T     A = V as it lies in memory (keys x head_dim = MN-major, two 64-wide atoms joined by LBO),
-//            B = P^T (MN-major).  Rows 0..79 of O^T are the head dims; row 80 multiplies a column of ONES the softmax threads
-//            plant in the V tile (head-dim slot 80), so the tensor core also delivers the softmax denominator: no second
-//            reduction over keys.  Rows 81..127 multiply whatever the 64-wide TMA box fetched past the head (finite) -- ignored.
+//   MMA2   O^T[128 x 64 q] = V^T P^T     A = V as it lies in memory (keys x head_dim = MN-major): THREE 32-wide 64-byte-swizzle atoms
+//            (head dims 0..95) joined by LBO; the instruction's fourth atom (rows 96..127) reads whatever follows in shared memory --
+//            an accumulator row depends on its own A row only, so garbage (even NaN) there never reaches a row that is read.
+//            B = P^T (MN-major, 128-byte swizzle).  Rows 0..79 of O^T are the head dims; row 80 multiplies a column of ONES the
+//            softmax threads plant in the V tile (head-dim slot 80), so the tensor core also delivers the softmax denominator: no
+//            second reduction over keys.  (Round-2 history: V as two 64-wide atoms cost 128 B per key and left room for ONE P^T
+//            buffer -- the in-kernel timeline showed the loop P^T(u) written -> MMA2(u) -> buffer free -> P^T(u+1) as the
+//            critical path, 5 100 cycles per unit; 96 B per key pays for the second buffer.)
 //   epilogue O^T / rowsum -> fp16 -> global, one query per store instruction (a warp writes 32 consecutive head dims = 64 B)
 // Warp roles (736 threads): 0 TMA producer of K + Q, 1 MMA issuer + TMEM allocator, 2 TMA producer of V, 4-19 softmax (two
 // groups of 8 warps, one per half of the 64 query columns; in a group warp w owns key tile w/4, TMEM sub-partition w%4),
@@ -40,7 +44,7 @@ struct TtParams {
     float scale_log2;
     __half* out;
     uint32_t off_k, k_bytes;        // nk_st x [Q64 8192 | K64 n1*128 | K16 n1*32 | Q16 2048] (padded to 1024)
-    uint32_t off_v, v_bytes;        // nv_st x [V[:, 0:64] n1*128 | V[:, 64:128] n1*128]
+    uint32_t off_v, v_bytes;        // nv_st x 3 atoms [V[:, 32a : 32a+32] n1*64]
     uint32_t off_p, p_bytes;        // npb x n1*128
     uint32_t off_red;               // partial column maxima (2 parities), final maxima, 2 x [64] softmax denominators
     uint32_t off_bar;
@@ -57,10 +61,30 @@ const char* const kTtEvents[] = {"k_issue", "v_issue", "k_ready", "s_issued", "p
 enum { BAR_KF = 0, BAR_KE = 2, BAR_VF = 4, BAR_VE = 6, BAR_SF = 8, BAR_SE = 10, BAR_PF = 12, BAR_PE = 14, BAR_OF = 16, BAR_OE = 18,
        BAR_COUNT = 20 };
 
+// epilogue store of one thread's head dim for `nq` consecutive queries (v[i] = O^T[hd][q0 + i], inv[i] = 1 / softmax denominator):
+// one 2-byte store per query row -- a warp covers 32 consecutive head dims = 64 contiguous bytes per instruction.  E_C != 0 makes the
+// row pitch a compile-time constant, so every store is [base + immediate] and the 32 multiply / convert / store triples are independent.
+template <int E_C>
+__device__ __forceinline__ void tt_store_rows(__half* dst, int E, const float (&v)[32], const float* inv, int nq) {
+    const int64_t ld = E_C ? E_C : E;
+    const float4* lf = reinterpret_cast<const float4*>(inv);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (4 * c < nq) {                                   // nq is a multiple of 16 (warp-uniform)
+            const float4 l4 = lf[c];
+            dst[(int64_t)(4 * c + 0) * ld] = __float2half_rn(v[4 * c + 0] * l4.x);
+            dst[(int64_t)(4 * c + 1) * ld] = __float2half_rn(v[4 * c + 1] * l4.y);
+            dst[(int64_t)(4 * c + 2) * ld] = __float2half_rn(v[4 * c + 2] * l4.z);
+            dst[(int64_t)(4 * c + 3) * ld] = __float2half_rn(v[4 * c + 3] * l4.w);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TT_THREADS, 1)
 attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
                     const __grid_constant__ CUtensorMap tm_s64, const __grid_constant__ CUtensorMap tm_s16,
-                    const __grid_constant__ CUtensorMap tm_c64, const __grid_constant__ CUtensorMap tm_c16, const TtParams p) {
+                    const __grid_constant__ CUtensorMap tm_c64, const __grid_constant__ CUtensorMap tm_c16,
+                    const __grid_constant__ CUtensorMap tm_sv, const __grid_constant__ CUtensorMap tm_cv, const TtParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -76,19 +100,21 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
     const int lane = threadIdx.x & 31;
     const int units = p.B * p.nhead;
     const int s_cols = p.n_mt * TT_Q;                // TMEM columns of one S^T accumulator set
+    const int ngrp = p.P > TT_QG ? TT_SM_GROUPS : 1;  // softmax groups with live query columns (<= 32 queries: group 0 alone)
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm_q64); ptx::prefetch_tensormap(&tm_q16);
         ptx::prefetch_tensormap(&tm_s64); ptx::prefetch_tensormap(&tm_s16);
         ptx::prefetch_tensormap(&tm_c64); ptx::prefetch_tensormap(&tm_c16);
+        ptx::prefetch_tensormap(&tm_sv); ptx::prefetch_tensormap(&tm_cv);
     }
     if (warp == 1) {
         if (lane == 0) {
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(bar(BAR_KF + i), 1); ptx::mbar_init(bar(BAR_KE + i), 1);
                 ptx::mbar_init(bar(BAR_VF + i), 1); ptx::mbar_init(bar(BAR_VE + i), 1);
-                ptx::mbar_init(bar(BAR_SF + i), 1); ptx::mbar_init(bar(BAR_SE + i), TT_SM_WARPS * TT_SM_GROUPS);
-                ptx::mbar_init(bar(BAR_PF + i), TT_SM_WARPS * TT_SM_GROUPS); ptx::mbar_init(bar(BAR_PE + i), 1);
+                ptx::mbar_init(bar(BAR_SF + i), 1); ptx::mbar_init(bar(BAR_SE + i), TT_SM_WARPS * ngrp);
+                ptx::mbar_init(bar(BAR_PF + i), TT_SM_WARPS * ngrp); ptx::mbar_init(bar(BAR_PE + i), 1);
                 ptx::mbar_init(bar(BAR_OF + i), 1); ptx::mbar_init(bar(BAR_OE + i), 3);
             }
             ptx::fence_barrier_init();
@@ -107,7 +133,7 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
     auto k_stage = [&](int st) { return smem_base + p.off_k + (uint32_t)st * p.k_bytes; };
     auto v_stage = [&](int st) { return smem_base + p.off_v + (uint32_t)st * p.v_bytes; };
     const uint32_t k64_off = TT_Q * 128u, k16_off = k64_off + (uint32_t)p.n1 * 128u, q16_off = k16_off + (uint32_t)p.n1 * 32u;
-    const uint32_t v_atom = (uint32_t)p.n1 * 128u;
+    const uint32_t v_atom = (uint32_t)p.n1 * 64u;              // one 32-head-dim atom of a V stage
 
     if (warp == 0) {
         // ===================== TMA producer: K and Q of a unit =====================
@@ -134,7 +160,7 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
             }
         }
     } else if (warp == 2) {
-        // ===================== TMA producer: V of a unit, as two 64-column boxes (the second runs past the head: see header) ======
+        // ===================== TMA producer: V of a unit, as three 32-column boxes (the third runs past the head: see header) ======
         if (lane == 0) {
             int uc = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
@@ -144,15 +170,14 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 ptx::mbar_wait(bar(BAR_VE + st), (((uint32_t)(uc / p.nv_st)) & 1u) ^ 1u);
                 const uint32_t fb = bar(BAR_VF + st);
                 trace_ev(p.trace, TR_TMAV, TE_V_ISSUE, uc);
-                ptx::mbar_arrive_expect_tx(fb, (uint32_t)(p.self_rows + p.sbox) * 256u);
-                const uint32_t va = v_stage(st), vb = va + v_atom;
+                ptx::mbar_arrive_expect_tx(fb, (uint32_t)(p.self_rows + p.sbox) * 192u);
+                const uint32_t va = v_stage(st);
                 const int hc = h * TT_HD;
-                if (p.self_rows) {
-                    ptx::tma_load_2d(&tm_s64, fb, va, 2 * p.E + hc, b * p.P);
-                    ptx::tma_load_2d(&tm_s64, fb, vb, 2 * p.E + hc + 64, b * p.P);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    if (p.self_rows) ptx::tma_load_2d(&tm_sv, fb, va + (uint32_t)a * v_atom, 2 * p.E + hc + 32 * a, b * p.P);
+                    ptx::tma_load_2d(&tm_cv, fb, va + (uint32_t)a * v_atom + (uint32_t)p.self_rows * 64u, p.E + hc + 32 * a, slot * p.S_max);
                 }
-                ptx::tma_load_2d(&tm_c64, fb, va + (uint32_t)p.self_rows * 128u, p.E + hc, slot * p.S_max);
-                ptx::tma_load_2d(&tm_c64, fb, vb + (uint32_t)p.self_rows * 128u, p.E + hc + 64, slot * p.S_max);
             }
         }
     } else if (warp == 1) {
@@ -198,8 +223,8 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 const uint32_t va = v_stage(st);
                 const uint32_t pt = smem_base + p.off_p + (uint32_t)pb * p.p_bytes;
                 const uint32_t d = tmem_base + col_o + (uint32_t)(ob * TT_Q);
-                uint64_t da = ptx::umma_desc_mn_sw128(va, v_atom), db = ptx::umma_desc_sw128(pt);
-                for (int ks = 0; ks < nks; ++ks, da += 128, db += 128)      // 16 keys = 2048 bytes further in both tiles (address field: >> 4)
+                uint64_t da = ptx::umma_desc_mn_sw64(va, v_atom), db = ptx::umma_desc_sw128(pt);
+                for (int ks = 0; ks < nks; ++ks, da += 64, db += 128)       // 16 keys = 1024 (V) / 2048 (P^T) bytes further (address field: >> 4)
                     ptx::umma_f16(d, da, db, idesc2, ks != 0);
                 ptx::umma_commit(bar(BAR_OF + ob));
                 ptx::umma_commit(bar(BAR_PE + pb));
@@ -217,6 +242,8 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
     } else if (warp >= 4 && warp < TT_EPI_WARP0) {
         // ===================== softmax down the lanes: S^T (TMEM) -> P^T (shared, fp16, MN-major 128B swizzle) =====================
         // two groups of 8 warps split the 64 query columns; inside a group warp sw owns key tile sw/4, TMEM sub-partition sw%4
+        // (with <= 32 queries the second group has no live column: its warps go straight to the final barrier, and the columns
+        //  32..63 of P^T / O^T hold garbage nobody reads -- an accumulator column depends on its own B column only)
         const int grp = (warp - 4) >> 3;
         const int sw = (warp - 4) & 7;
         const int mt = sw >> 2;
@@ -225,7 +252,7 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
         const int bar_id = 1 + grp;
         float* fin = colfin + (grp * TT_SM_WARPS + sw) * TT_QG;
         int uc = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
+        for (int u = grp < ngrp ? blockIdx.x : units; u < units; u += gridDim.x, ++uc) {
             const int b = u / p.nhead;
             const int slot = p.kv_slot ? p.kv_slot[b] : b;
             const int nk = p.self_rows + (p.kv_len ? p.kv_len[slot] : p.S_max);
@@ -281,8 +308,9 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 }
                 if (grp == 0) {
                     // head-dim slot 80 of this key's V row := 1 (81..87 := 0): row 80 of O^T becomes the softmax denominator
-                    uint8_t* vrow = smem_gen + p.off_v + (size_t)vst * p.v_bytes + v_atom + (size_t)j * 128;
-                    *reinterpret_cast<uint4*>(vrow + ((2 ^ (j & 7)) << 4)) = make_uint4(0x00003C00u, 0u, 0u, 0u);
+                    // (third atom = head dims 64..95, 64-byte rows: slot 80 is 16-byte chunk 2, swizzled with address bits 7..8)
+                    uint8_t* vrow = smem_gen + p.off_v + (size_t)vst * p.v_bytes + 2 * v_atom + (size_t)j * 64;
+                    *reinterpret_cast<uint4*>(vrow + ((2 ^ ((j >> 1) & 3)) << 4)) = make_uint4(0x00003C00u, 0u, 0u, 0u);
                 }
             }
             ptx::tc_fence_before();
@@ -298,6 +326,7 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
         // ===================== epilogue: O^T (TMEM) / rowsum -> fp16 -> global =====================
         const int wq = warp & 3;                        // sub-partition = head dims 32*wq ..
         const int hd = wq * 32 + lane;
+        const int nhf = p.P > 32 ? 2 : 1;               // 32-query halves of the accumulator that carry live queries
         int uc = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
             const int b = u / p.nhead, h = u - b * p.nhead;
@@ -308,9 +337,10 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
             const uint32_t to = tmem_base + ((uint32_t)(wq * 32) << 16) + col_o + (uint32_t)(ob * TT_Q);
             float* ls = lsum + ob * TT_Q;
             float v[32];
-            if (wq == 2) {                              // row 80 (this warp's lane 16) = sum over keys of P^T (the ones column of V)
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
+            if (wq == 2) {
+                // row 80 (this warp's lane 16) = sum over keys of P^T (the ones column of V); the warp turns the 64 sums into
+                // reciprocals once, so the store loop below is multiply / convert / store with no dependent MUFU in between
+                for (int hf = 0; hf < nhf; ++hf) {
                     ptx::tmem_ld_32x32(to + (uint32_t)(hf * 32), v);
                     if (hd == TT_HD) {
 #pragma unroll
@@ -318,28 +348,25 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                             *reinterpret_cast<float4*>(ls + hf * 32 + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
                     }
                 }
+                __syncwarp();
+                const float i0 = 1.0f / ls[lane], i1 = nhf > 1 ? 1.0f / ls[32 + lane] : 0.f;
+                __syncwarp();
+                ls[lane] = i0;
+                if (nhf > 1) ls[32 + lane] = i1;
             }
             ptx::bar_sync(3, 96);
             __half* dst = p.out + (int64_t)b * p.P * p.E + h * TT_HD + hd;
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
+            for (int hf = 0; hf < nhf; ++hf) {
                 ptx::tmem_ld_32x32(to + (uint32_t)(hf * 32), v);
-                if (hf == 1) {                          // the accumulator has been read: MMA2 of unit uc+2 may overwrite it
+                if (hf == nhf - 1) {                    // the accumulator has been read: MMA2 of unit uc+2 may overwrite it
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(bar(BAR_OE + ob));
                 }
                 if (hd < TT_HD) {
-                    const float4* lf = reinterpret_cast<const float4*>(ls + hf * 32);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float4 l4 = lf[c];
-                        const int q = hf * 32 + 4 * c;
-                        if (q + 0 < p.P) dst[(int64_t)(q + 0) * p.E] = __float2half_rn(__fdividef(v[4 * c + 0], l4.x));
-                        if (q + 1 < p.P) dst[(int64_t)(q + 1) * p.E] = __float2half_rn(__fdividef(v[4 * c + 1], l4.y));
-                        if (q + 2 < p.P) dst[(int64_t)(q + 2) * p.E] = __float2half_rn(__fdividef(v[4 * c + 2], l4.z));
-                        if (q + 3 < p.P) dst[(int64_t)(q + 3) * p.E] = __float2half_rn(__fdividef(v[4 * c + 3], l4.w));
-                    }
+                    const int nq = p.P - hf * 32 < 32 ? p.P - hf * 32 : 32;
+                    if (p.E == 1280) tt_store_rows<1280>(dst + (int64_t)hf * 32 * 1280, 1280, v, ls + hf * 32, nq);
+                    else tt_store_rows<0>(dst + (int64_t)hf * 32 * p.E, p.E, v, ls + hf * 32, nq);
                 }
             }
             if (wq == 0 && lane == 0) trace_ev(p.trace, TR_EPI, TE_O_DONE, uc);
@@ -351,7 +378,7 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
 }
 
 int tt_tmap(const void* ptr, int64_t rows, int64_t cols, int box_cols, int box_rows, CUtensorMap* out) {
-    return cached_tmap_f16_2d(ptr, rows, cols, cols, box_cols, box_rows, box_cols == 64 ? 128 : 32, out);
+    return cached_tmap_f16_2d(ptr, rows, cols, cols, box_cols, box_rows, 2 * box_cols, out);      // one swizzle span per box row
 }
 
 }  // namespace
@@ -374,11 +401,11 @@ int launch_attention_tt(const AttnParams& a, cudaStream_t st) {
     p.n_mt = (p.n1 + 127) / 128;
     p.kv_len = a.kv_len; p.kv_slot = a.kv_slot; p.scale_log2 = a.scale_log2; p.out = a.out;
     p.k_bytes = ((uint32_t)(TT_Q * 160 + p.n1 * 160) + 1023u) & ~1023u;
-    p.v_bytes = (uint32_t)p.n1 * 256u;
+    p.v_bytes = (uint32_t)p.n1 * 192u;
     p.p_bytes = (uint32_t)p.n1 * 128u;
     const uint32_t red_bytes = (2 * TT_SM_GROUPS * TT_SM_WARPS * TT_QG + TT_SM_GROUPS * TT_SM_WARPS * TT_QG + 2 * TT_Q) * 4;
-    // MMA1 reads whole 128-row key tiles: the rows past n1 are whatever follows in shared memory (masked by the softmax), so
-    // the K stages come first and everything the over-read can touch lies inside the allocation
+    // MMA1 reads whole 128-row key tiles (the rows past n1 are masked by the softmax) and MMA2 a fourth V atom (rows nobody
+    // reads): whatever follows in shared memory.  K stages first, then V, then P^T: every over-read stays inside the allocation
     const uint32_t fixed = red_bytes + 8 * (BAR_COUNT + 1) + 1024 /*alignment slack*/;
     const uint32_t cap = 227 * 1024;
     p.nk_st = 2; p.nv_st = 2; p.npb = 2;
@@ -396,7 +423,7 @@ int launch_attention_tt(const AttnParams& a, cudaStream_t st) {
 
     if (a.B == 0 || a.P == 0) return 0;
     const int64_t q_rows = (int64_t)a.B * a.P;
-    CUtensorMap tq64, tq16, ts64, ts16, tc64, tc16;
+    CUtensorMap tq64, tq16, ts64, ts16, tc64, tc16, tsv, tcv;
     PB_TRY(tt_tmap(a.qkv, q_rows, 3 * (int64_t)a.E, 64, TT_Q, &tq64));
     PB_TRY(tt_tmap(a.qkv, q_rows, 3 * (int64_t)a.E, 16, TT_Q, &tq16));
     const int sr = p.self_rows ? p.self_rows : 8;
@@ -405,6 +432,8 @@ int launch_attention_tt(const AttnParams& a, cudaStream_t st) {
     const int64_t c_rows = (int64_t)(a.n_slots > 0 ? a.n_slots : a.B) * a.S_max;
     PB_TRY(tt_tmap(a.ckv, c_rows, 2 * (int64_t)a.E, 64, p.sbox, &tc64));
     PB_TRY(tt_tmap(a.ckv, c_rows, 2 * (int64_t)a.E, 16, p.sbox, &tc16));
+    PB_TRY(tt_tmap(a.qkv, q_rows, 3 * (int64_t)a.E, 32, sr, &tsv));
+    PB_TRY(tt_tmap(a.ckv, c_rows, 2 * (int64_t)a.E, 32, p.sbox, &tcv));
 
     static DeviceOnce attr;
     if (attr.first()) PB_CUDA(cudaFuncSetAttribute(attention_tt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -412,7 +441,7 @@ int launch_attention_tt(const AttnParams& a, cudaStream_t st) {
     const int units = a.B * a.nhead;
     const int grid = units < sm_count() ? units : sm_count();
     p.trace = a.P == 64 ? trace_begin("attention_tt") : TraceBuf{nullptr};
-    attention_tt_kernel<<<grid, TT_THREADS, smem, st>>>(tq64, tq16, ts64, ts16, tc64, tc16, p);
+    attention_tt_kernel<<<grid, TT_THREADS, smem, st>>>(tq64, tq16, ts64, ts16, tc64, tc16, tsv, tcv, p);
     PB_LAUNCH_CHECK();
     if (p.trace.buf) PB_TRY(trace_end("attention_tt", p.trace, kTtRoles, kTtEvents));
     return 0;

@@ -72,7 +72,7 @@ int make_tmap_f16_2d_box(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t
     PB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
     PB_CHECK(((uintptr_t)ptr & 15) == 0, "TMA: base pointer must be 16-byte aligned");
     PB_CHECK((ld * 2) % 16 == 0, "TMA: row stride %lld halves is not a multiple of 16 bytes", (long long)ld);
-    PB_CHECK(swizzle_bytes == 128 || swizzle_bytes == 32 || swizzle_bytes == 0, "TMA: swizzle %d unsupported", swizzle_bytes);
+    PB_CHECK(swizzle_bytes == 128 || swizzle_bytes == 64 || swizzle_bytes == 32 || swizzle_bytes == 0, "TMA: swizzle %d unsupported", swizzle_bytes);
     PB_CHECK(box_rows >= 1 && box_rows <= 256 && box_cols >= 8 && (swizzle_bytes == 0 ? box_cols <= 256 : box_cols * 2 <= swizzle_bytes),
              "TMA: bad box %dx%d for swizzle %d", box_rows, box_cols, swizzle_bytes);
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -81,7 +81,8 @@ int make_tmap_f16_2d_box(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                    swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                    : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(box %dx%d, swizzle %d) failed (%d)", box_rows, box_cols, swizzle_bytes, (int)r);
     return 0;

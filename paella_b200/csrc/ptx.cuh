@@ -300,6 +300,13 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     return d;
 }
+// same with 32-element (64-byte) swizzle atoms: canonical layout ((8,4,m),(8,k)):((1,8,LBO),(32,SBO)), SBO = 8 rows * 64 B
+__device__ __forceinline__ uint64_t umma_desc_mn_sw64(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = umma_desc(smem_addr, 512, 4);
+    d &= ~((uint64_t)0x3FFF << 16);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    return d;
+}
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) { return umma_desc(smem_addr, 1024, 2); }
 __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) { return umma_desc(smem_addr, 256, 6); }
 
