@@ -80,6 +80,12 @@ __device__ __forceinline__ void tt_store_rows(__half* dst, int E, const float (&
     }
 }
 
+// producer-side wait: the TMA warps are never latency-critical (their stages are released a whole unit ahead), so they sleep between
+// polls instead of competing for issue slots with the softmax warps of their SM sub-partition
+__device__ __forceinline__ void tt_wait_relaxed(uint32_t bar, uint32_t parity) {
+    while (!ptx::mbar_try_wait(bar, parity)) __nanosleep(200);
+}
+
 __global__ void __launch_bounds__(TT_THREADS, 1)
 attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
                     const __grid_constant__ CUtensorMap tm_s64, const __grid_constant__ CUtensorMap tm_s16,
@@ -143,7 +149,7 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 const int b = u / p.nhead, h = u - b * p.nhead;
                 const int slot = p.kv_slot ? p.kv_slot[b] : b;
                 const int st = uc % p.nk_st;
-                ptx::mbar_wait(bar(BAR_KE + st), (((uint32_t)(uc / p.nk_st)) & 1u) ^ 1u);
+                tt_wait_relaxed(bar(BAR_KE + st), (((uint32_t)(uc / p.nk_st)) & 1u) ^ 1u);
                 const uint32_t fb = bar(BAR_KF + st);
                 trace_ev(p.trace, TR_TMA, TE_K_ISSUE, uc);
                 ptx::mbar_arrive_expect_tx(fb, (uint32_t)(p.self_rows + p.sbox + TT_Q) * 160u);
@@ -167,7 +173,7 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 const int b = u / p.nhead, h = u - b * p.nhead;
                 const int slot = p.kv_slot ? p.kv_slot[b] : b;
                 const int st = uc % p.nv_st;
-                ptx::mbar_wait(bar(BAR_VE + st), (((uint32_t)(uc / p.nv_st)) & 1u) ^ 1u);
+                tt_wait_relaxed(bar(BAR_VE + st), (((uint32_t)(uc / p.nv_st)) & 1u) ^ 1u);
                 const uint32_t fb = bar(BAR_VF + st);
                 trace_ev(p.trace, TR_TMAV, TE_V_ISSUE, uc);
                 ptx::mbar_arrive_expect_tx(fb, (uint32_t)(p.self_rows + p.sbox) * 192u);

@@ -399,6 +399,162 @@ static int dwconv3_patch_launch(const float* x, const float* skip, const float* 
     return 0;
 }
 
+// ------------------------------------------------------------------ codec ResBlock front, fused (ref/src/vqgan.py:36-40)
+//   x' = x + g2 * (dw3x3(ReplicationPad(LN(x) * (1 + g0) + g1)) + bias);   a16 = fp16(LN(x') * (1 + g3) + g4)
+// Three launches (LayerNorm -> fp32 copy, depthwise + residual, LayerNorm -> fp16) moved 26 bytes per element; here a warp-per-row
+// statistics pre-pass (mean, rstd of every position: 4 B read per element) feeds ONE patch kernel that normalises the halo values
+// on the fly (LayerNorm is affine per position), keeps the 2 x 8 patch in registers, adds the residual and reduces the second
+// LayerNorm's statistics inside the CTA (thread = 4 channels, like dwconv3_ln_patch_kernel): 4 + 4 + 4 + 2 = 14 bytes per element.
+// x' goes to a SECOND buffer (neighbouring CTAs still read the old x for their halos); the MLP's second GEMM reads it as the
+// residual and writes the block's output back into the original buffer.
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, int64_t rows, int C, float2* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+    const int nv = C >> 2;
+    float s = 0.f;
+    for (int i = lane; i < nv; i += 32) { const float4 v = xr[i]; s += (v.x + v.y) + (v.z + v.w); }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+        const float4 v = xr[i];
+        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = ln_rstd(warp_sum(q) / C);
+    if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) vq_front_patch_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
+                                                              const float* __restrict__ wp, const float* __restrict__ bias,
+                                                              float a0, float g1, float g2, float a3, float g4, int B, int h, int w,
+                                                              int c, float* __restrict__ x_out, __half* __restrict__ a16) {
+    __shared__ float red[32 * DW_NPOS];
+    __shared__ float tot[2][DW_NPOS];
+    __shared__ float2 st_s[DW_PH + 2][DW_PW + 2];
+    const int q = threadIdx.x, nvq = c >> 2;
+    const bool active = q < nvq;
+    const int qc = active ? q : 0;                       // idle threads shadow chunk 0 and never store
+    const int tiles_x = (w + DW_PW - 1) / DW_PW, tiles_y = (h + DW_PH - 1) / DW_PH;
+    const int b = blockIdx.x / (tiles_x * tiles_y);
+    const int tr = blockIdx.x - b * (tiles_x * tiles_y);
+    const int y0 = (tr / tiles_x) * DW_PH, x0 = (tr % tiles_x) * DW_PW;
+    auto cy = [&](int y) { return min(max(y, 0), h - 1); };           // ReplicationPad2d(1) = clamped coordinates
+    auto cx = [&](int xx) { return min(max(xx, 0), w - 1); };
+    if (threadIdx.x < (DW_PH + 2) * (DW_PW + 2)) {
+        const int r = threadIdx.x / (DW_PW + 2), j = threadIdx.x - r * (DW_PW + 2);
+        st_s[r][j] = stats[((int64_t)b * h + cy(y0 - 1 + r)) * w + cx(x0 - 1 + j)];
+    }
+    __syncthreads();
+
+    float4 acc[DW_PH][DW_PW];
+    {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + qc);
+#pragma unroll
+        for (int oy = 0; oy < DW_PH; ++oy)
+#pragma unroll
+            for (int ox = 0; ox < DW_PW; ++ox) acc[oy][ox] = bv;
+    }
+#pragma unroll
+    for (int r = 0; r < DW_PH + 2; ++r) {
+        float4 wt[DW_PH][3];
+#pragma unroll
+        for (int oy = 0; oy < DW_PH; ++oy) {
+            const int ky = r - oy;
+            if (ky < 0 || ky > 2) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) wt[oy][kx] = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)(ky * 3 + kx) * c) + qc);
+        }
+        const int64_t rowbase = ((int64_t)b * h + cy(y0 - 1 + r)) * w;
+#pragma unroll
+        for (int j = 0; j < DW_PW + 2; ++j) {
+            const float4 v = *(reinterpret_cast<const float4*>(x + (rowbase + cx(x0 - 1 + j)) * c) + qc);
+            const float2 ms = st_s[r][j];
+            const float sc = ms.y * a0;                   // the first LayerNorm's scalar affine, as launch_ln_rows applies it
+            const float4 t = make_float4(fmaf(v.x - ms.x, sc, g1), fmaf(v.y - ms.x, sc, g1), fmaf(v.z - ms.x, sc, g1), fmaf(v.w - ms.x, sc, g1));
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ox = j - kx;
+                if (ox < 0 || ox >= DW_PW) continue;
+#pragma unroll
+                for (int oy = 0; oy < DW_PH; ++oy) {
+                    const int ky = r - oy;
+                    if (ky < 0 || ky > 2) continue;
+                    fma4(acc[oy][ox], t, wt[oy][kx]);
+                }
+            }
+        }
+    }
+    // ---- residual: x' = x + g2 * conv (the centre values come back from L1)
+#pragma unroll
+    for (int p = 0; p < DW_NPOS; ++p) {
+        const float4 xc = *(reinterpret_cast<const float4*>(x + (((int64_t)b * h + cy(y0 + p / DW_PW)) * w + cx(x0 + p % DW_PW)) * c) + qc);
+        float4& a = acc[p / DW_PW][p % DW_PW];
+        a.x = fmaf(a.x, g2, xc.x); a.y = fmaf(a.y, g2, xc.y); a.z = fmaf(a.z, g2, xc.z); a.w = fmaf(a.w, g2, xc.w);
+    }
+    // ---- second LayerNorm over channels for the 16 positions (two-pass, like F.layer_norm)
+    const int n_warps = blockDim.x >> 5;
+    float s[DW_NPOS];
+#pragma unroll
+    for (int p = 0; p < DW_NPOS; ++p) {
+        const float4 a = acc[p / DW_PW][p % DW_PW];
+        s[p] = active ? (a.x + a.y) + (a.z + a.w) : 0.f;
+    }
+    block_sum16(s, red, tot[0], n_warps);
+    const float inv_c = 1.0f / c;
+#pragma unroll
+    for (int p = 0; p < DW_NPOS; ++p) {
+        const float mean = tot[0][p] * inv_c;
+        const float4 a = acc[p / DW_PW][p % DW_PW];
+        const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+        s[p] = active ? (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) : 0.f;
+    }
+    block_sum16(s, red, tot[1], n_warps);
+    if (!active) return;
+#pragma unroll
+    for (int p = 0; p < DW_NPOS; ++p) {
+        const int y = y0 + p / DW_PW, xx = x0 + p % DW_PW;
+        if (y >= h || xx >= w) continue;
+        const float mean = tot[0][p] * inv_c;
+        const float rstd = ln_rstd(tot[1][p] * inv_c) * a3;
+        const float4 a = acc[p / DW_PW][p % DW_PW];
+        const int64_t o = (((int64_t)b * h + y) * w + xx) * c + q * 4;
+        *reinterpret_cast<float4*>(x_out + o) = a;
+        uint2 pk;
+        pk.x = pack_half2(fmaf(a.x - mean, rstd, g4), fmaf(a.y - mean, rstd, g4));
+        pk.y = pack_half2(fmaf(a.z - mean, rstd, g4), fmaf(a.w - mean, rstd, g4));
+        *reinterpret_cast<uint2*>(a16 + o) = pk;
+    }
+}
+
+bool vq_front_fused_ok(int c, int h, int w) { return c % 4 == 0 && c >= 4 * (DW_PH + 2) * (DW_PW + 2) && c <= 512 && h >= 1 && w >= 1; }
+
+int launch_vq_front_fused(const float* x, int B, int h, int w, int c, const float* w9, const float* bias, const float* gam,
+                          float2* stats_scratch, float* x_out, __half* a16, cudaStream_t st) {
+    PB_CHECK(vq_front_fused_ok(c, h, w), "vq_front: width %d not handled by the patch kernel", c);
+    const int64_t M = (int64_t)B * h * w;
+    if (M == 0) return 0;
+    {
+        ProfScope prof("vq_rowstats", (double)M * c * 4.0, st);
+        row_stats_kernel<<<ceil_div(M, 8), 256, 0, st>>>(x, M, c, stats_scratch);
+        PB_LAUNCH_CHECK();
+    }
+    ProfScope prof("vq_front", (double)M * c * 10.0, st);
+    const int64_t grid = (int64_t)B * ceil_div(h, DW_PH) * ceil_div(w, DW_PW);
+    PB_CHECK(grid < (1ll << 31), "vq_front: grid too large");
+    const int threads = ceil_div(c / 4, 32) * 32;
+    // 3 CTAs of 96 threads per SM at 168 registers; capping at 128 registers for a fourth CTA spilled 376 B per thread and measured
+    // 6.25 vs 5.73 ms per bs=64 round trip (profiles/r02j_*)
+    if (threads <= 64)
+        vq_front_patch_kernel<64, 6><<<(unsigned)grid, threads, 0, st>>>(x, stats_scratch, w9, bias, 1.0f + gam[0], gam[1], gam[2], 1.0f + gam[3], gam[4], B, h, w, c, x_out, a16);
+    else
+        vq_front_patch_kernel<128, 3><<<(unsigned)grid, threads, 0, st>>>(x, stats_scratch, w9, bias, 1.0f + gam[0], gam[1], gam[2], 1.0f + gam[3], gam[4], B, h, w, c, x_out, a16);
+    PB_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int NV>
 static int dwconv_dispatch(const float* x, const float* skip, const float* wp, const float* bias, int B, int h, int w,
                            int c, int k, __half* out, cudaStream_t st) {

@@ -22,6 +22,12 @@ int launch_ln_patchify2(const float* x, int B, int h, int w, int c, __half* out,
 int launch_dwconv_ln(const float* x, const float* skip, const float* w_packed, const float* bias, int B, int h, int w,
                      int c, int k, __half* out, cudaStream_t st);
 
+// codec ResBlock front in one pass (ref/src/vqgan.py:36-40; see ops.cu): x' = x + g2*(dw3x3(reppad(LN(x)(1+g0)+g1)) + bias) -> x_out
+// (a buffer other than x), a16 = fp16(LN(x')(1+g3)+g4).  gam = the block's gammas on the HOST; stats_scratch: B*h*w float2.
+bool vq_front_fused_ok(int c, int h, int w);
+int launch_vq_front_fused(const float* x, int B, int h, int w, int c, const float* w9, const float* bias, const float* gam,
+                          float2* stats_scratch, float* x_out, __half* a16, cudaStream_t st);
+
 // GlobalResponseNorm: h[b,p,n] = h*(1 + gamma[n]*Gx[b,n]/(mean_n Gx + 1e-6)) + beta[n], Gx = sqrt(sq[b,n]) (2^-24 fixed point);
 // zeroes all B*zero_per_sample entries of sq_next (the other buffer of a ping-pong pair) for the next block.
 // scale_scratch: fp32 [B, N] (the per-sample multipliers, written by the first of the two launches)

@@ -327,11 +327,19 @@ static void vq_plan(const pb200_vqgan* m, int B, int H, int W, uint8_t* base, in
     ws.idx = (int64_t*)take(M1 * 8);
 }
 
-// The part of a codec ResBlock (ref/src/vqgan.py:36-42) before its MLP: x += g2 * dw3x3(pad(LN(x)(1+g0)+g1)), then
-// a16 = fp16(LN(x)(1+g3)+g4).  x: NHWC fp32 [B,h,w,c], updated in place.
+// The part of a codec ResBlock (ref/src/vqgan.py:36-42) before its MLP: x' = x + g2 * dw3x3(pad(LN(x)(1+g0)+g1)), then
+// a16 = fp16(LN(x')(1+g3)+g4).  x: NHWC fp32 [B,h,w,c].  *resid = where x' lives: `tmp32` on the fused path (one patch kernel +
+// a statistics pre-pass, ops.cu::launch_vq_front_fused; `scratch` = B*h*w float2), x itself (updated in place) on the three-launch
+// path that narrow widths (tiny test codecs) and in_place = true (the fused-MLP experiment) take.
 static int resblock_front(float* x, int B, int h, int w, int c, const float* dw_w9, const float* dw_b, const float* gam,
-                          float* tmp32, __half* a16, cudaStream_t st) {
+                          float* tmp32, __half* a16, void* scratch, bool in_place, const float** resid, cudaStream_t st) {
     const int64_t M = (int64_t)B * h * w;
+    static const bool unfused = getenv("PB200_VQ_FRONT_UNFUSED") != nullptr;      // A/B knob
+    if (!in_place && !unfused && vq_front_fused_ok(c, h, w)) {
+        *resid = tmp32;
+        return launch_vq_front_fused(x, B, h, w, c, dw_w9, dw_b, gam, reinterpret_cast<float2*>(scratch), tmp32, a16, st);
+    }
+    *resid = x;
     PB_TRY(launch_ln_rows(x, M, c, 1.0f + gam[0], gam[1], nullptr, tmp32, st));
     {
         ProfScope prof("vq_dwconv", (double)M * c * 12.0, st);
@@ -345,8 +353,10 @@ static int resblock_front(float* x, int B, int h, int w, int c, const float* dw_
 static int run_resblock(pb200_vqgan* m, const VqResBlock& rb, float* x, int B, int h, int w, VqWs& ws, cudaStream_t st) {
     const int c = rb.c;
     const int64_t M = (int64_t)B * h * w;
-    PB_TRY(resblock_front(x, B, h, w, c, m->w<float>(rb.dw_w), m->w<float>(rb.dw_b), rb.gam, ws.tmp32, ws.a16, st));
     static const bool fused = getenv("PB200_VQ_MLP_FUSED") != nullptr;      // experiment knob: see vq_mlp.cu (measured slower)
+    const float* resid = x;
+    // (h16 is idle until GEMM1 writes it: it lends its first bytes to the row statistics)
+    PB_TRY(resblock_front(x, B, h, w, c, m->w<float>(rb.dw_w), m->w<float>(rb.dw_b), rb.gam, ws.tmp32, ws.a16, ws.h16, fused, &resid, st));
     if (fused) {    // Linear -> GELU -> Linear -> x + g5 * (.) in one kernel, the 4c hidden never leaves the SM
         const int rc = launch_vq_mlp_fused(ws.a16, M, c, m->w<__half>(rb.w1), m->w<float>(rb.b1), m->w<__half>(rb.w2), m->w<float>(rb.b2), x,
                                            rb.gam[5], st);
@@ -355,7 +365,7 @@ static int run_resblock(pb200_vqgan* m, const VqResBlock& rb, float* x, int B, i
     pb200_gemm_epilogue e1 = vepi(PB200_EPI_GELU_F16, m->w<float>(rb.b1), ws.h16, 4 * c);
     PB_TRY(m->gemm(ws.a16, c, M, c, rb.w1, 4 * (int64_t)c, e1, st));
     pb200_gemm_epilogue e2 = vepi(PB200_EPI_RESID_F32, m->w<float>(rb.b2), x, c);
-    e2.resid = x; e2.ldr = c; e2.alpha = rb.gam[5];
+    e2.resid = resid; e2.ldr = c; e2.alpha = rb.gam[5];
     PB_TRY(m->gemm(ws.h16, 4 * (int64_t)c, M, 4 * (int64_t)c, rb.w2, c, e2, st));
     return 0;
 }
@@ -391,11 +401,12 @@ int pb200_vqgan_resblock(float* x_nhwc, int batch, int h, int w, int c, const fl
     float* tmp32 = reinterpret_cast<float*>(base);
     __half* a16 = reinterpret_cast<__half*>(base + up(M * c * 4));
     __half* h16 = reinterpret_cast<__half*>(base + up(M * c * 4) + up(M * c * 2));
-    PB_TRY(resblock_front(x_nhwc, batch, h, w, c, dw_w9, dw_bias, gammas_host, tmp32, a16, st));
+    const float* resid = x_nhwc;
+    PB_TRY(resblock_front(x_nhwc, batch, h, w, c, dw_w9, dw_bias, gammas_host, tmp32, a16, h16, false, &resid, st));
     pb200_gemm_epilogue e1 = vepi(PB200_EPI_GELU_F16, b1, h16, 4 * c);
     PB_TRY(gemm_f16(a16, c, w1_f16, c, M, 4 * (int64_t)c, c, e1, st));
     pb200_gemm_epilogue e2 = vepi(PB200_EPI_RESID_F32, b2, x_nhwc, c);
-    e2.resid = x_nhwc; e2.ldr = c; e2.alpha = gammas_host[5];
+    e2.resid = resid; e2.ldr = c; e2.alpha = gammas_host[5];
     return gemm_f16(h16, 4 * (int64_t)c, w2_f16, 4 * (int64_t)c, M, c, 4 * (int64_t)c, e2, st);
 }
 

@@ -408,7 +408,7 @@ def test_packed_checkpoint_roundtrip(tmp_path, f4):
         VQModel.from_packed(str(tmp_path / "bad.pb200"), DEV)
 
 
-@pytest.mark.parametrize("c,hw", [(384, 16), (192, 24), (32, 5)])
+@pytest.mark.parametrize("c,hw", [(384, 16), (192, 24), (32, 5), (192, 13), (384, 9)])     # 13, 9: partial 2x8 patches, clamped halos
 def test_vqgan_resblock_standalone_vs_oracle(c, hw):
     """R15: vqgan.ResBlock.forward on its own (ref/src/vqgan.py:36-42) vs the oracle's restatement."""
     from oracle import vqgan_oracle as vo
