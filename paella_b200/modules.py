@@ -685,12 +685,20 @@ class Paella(nn.Module):
             vers = tuple(None if t is None else t._version for t in ts)
         except RuntimeError:        # inference tensors carry no version counter: no memo
             vers = None
-        memo = self._cond_single
-        if (vers is not None and memo is not None and memo["hw"] == tuple(hw) and memo["vers"] == vers and len(memo["ts"]) == len(ts)
-                and all(a is b for a, b in zip(memo["ts"], ts)) and memo["key"] == self._packed_key):
-            return memo["cond"]
+        # a few entries, most recent first: the loop alternates between the conditional and the unconditional inputs
+        memos = self._cond_single if isinstance(self._cond_single, list) else []
+        if vers is not None:
+            for i, memo in enumerate(memos):
+                if (memo["hw"] == tuple(hw) and memo["vers"] == vers and len(memo["ts"]) == len(ts)
+                        and all(a is b for a, b in zip(memo["ts"], ts)) and memo["key"] == self._packed_key):
+                    if i:
+                        memos.insert(0, memos.pop(i))
+                    return memo["cond"]
         cond = self.prepare_conditioning([{"byt5": byt5, "clip": clip, "clip_image": clip_image}], hw, share_uniform=False)
-        self._cond_single = None if vers is None else {"hw": tuple(hw), "vers": vers, "ts": ts, "cond": cond, "key": self._packed_key}
+        if vers is not None:
+            memos.insert(0, {"hw": tuple(hw), "vers": vers, "ts": ts, "cond": cond, "key": self._packed_key})
+            del memos[4:]
+            self._cond_single = memos
         return cond
 
     def add_noise(self, x, t, mask=None, random_x=None):

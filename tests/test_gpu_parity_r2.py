@@ -240,15 +240,22 @@ def test_forward_memoises_conditioning_for_the_reference_loop(default_model):
     x = torch.randint(0, 8192, (1, 16, 16), device=DEV, generator=g)
     r = torch.tensor([0.5], device=DEV)
     a = m(x, r, byt5, clip=clip)
-    memo = m._cond_single
-    assert memo is not None
+    first = m._cond_single[0]["cond"]
     b = m(x, r, byt5, clip=clip)
-    assert m._cond_single is memo and torch.equal(a, b)
+    assert m._cond_single[0]["cond"] is first and torch.equal(a, b)
+    # the loop alternates conditional / unconditional inputs: both stay memoised
+    zb, zc = torch.zeros_like(byt5), torch.zeros_like(clip)
+    u0 = m(x, r, zb, clip=zc)
+    second = m._cond_single[0]["cond"]
+    assert second is not first
+    assert torch.equal(m(x, r, byt5, clip=clip), a) and m._cond_single[0]["cond"] is first
+    assert torch.equal(m(x, r, zb, clip=zc), u0) and m._cond_single[0]["cond"] is second
     byt5.mul_(2.0)                                    # in-place edit: version counter moves
     c = m(x, r, byt5, clip=clip)
-    assert m._cond_single is not memo and not torch.equal(a, c)
+    assert m._cond_single[0]["cond"] is not first and not torch.equal(a, c)
     d = m(x, r, byt5.clone(), clip=clip)              # equal content in a new tensor: rebuilt, same result
     assert torch.equal(c, d)
+    assert len(m._cond_single) <= 4
 
 
 def test_sample_distributed_options_vs_oracle_teacher_forced():
