@@ -17,9 +17,9 @@
 //            buffer -- the in-kernel timeline showed the loop P^T(u) written -> MMA2(u) -> buffer free -> P^T(u+1) as the
 //            critical path, 5 100 cycles per unit; 96 B per key pays for the second buffer.)
 //   epilogue O^T / rowsum -> fp16 -> global, one query per store instruction (a warp writes 32 consecutive head dims = 64 B)
-// Warp roles (736 threads): 0 TMA producer of K + Q, 1 MMA issuer + TMEM allocator, 2 TMA producer of V, 4-19 softmax (two
-// groups of 8 warps, one per half of the 64 query columns; in a group warp w owns key tile w/4, TMEM sub-partition w%4),
-// 20-22 epilogue (sub-partitions 0..2 = head dims 0..95).
+// Warp roles (736 threads): 0 TMA producer of K + Q, 2 TMA producer of V, 3 MMA issuer + TMEM allocator (1 idle), 4-19 softmax (two
+// groups of 8 warps working on ALTERNATE units, half a period apart; in a group warp w owns key tile w/4, TMEM sub-partition
+// w%4, and walks the 64 query columns in two passes of 32), 20-22 epilogue (sub-partitions 0..2 = head dims 0..95).
 // Shapes this kernel does not take (attn_weights, > 64 queries, > 256 keys) fall through to attention_tc.cu / attention.cu.
 #include "attention.cuh"
 #include "gemm.cuh"
@@ -29,9 +29,10 @@ namespace {
 
 constexpr int TT_HD = 80;
 constexpr int TT_Q = 64;
-constexpr int TT_SM_WARPS = 8;             // softmax warps per column group: 2 key tiles x 4 TMEM sub-partitions
-constexpr int TT_SM_GROUPS = 2;            // column (query) halves, one group of 8 warps each
-constexpr int TT_QG = TT_Q / TT_SM_GROUPS;  // 32 queries per group
+constexpr int TT_SM_WARPS = 8;             // softmax warps per group: 2 key tiles x 4 TMEM sub-partitions
+constexpr int TT_SM_GROUPS = 2;            // softmax groups: they take alternate units (group g = S^T / P^T / V stage g)
+constexpr int TT_QG = 32;                  // query columns per pass (one 32x32b TMEM load)
+constexpr int TT_MMA_WARP = 3;             // SM sub-partition 3: the one without a TMA producer or an epilogue warp (warp 1 idles)
 constexpr int TT_EPI_WARP0 = 4 + TT_SM_WARPS * TT_SM_GROUPS;      // 20: a multiple of 4 (TMEM sub-partition = warp % 4)
 constexpr int TT_THREADS = (TT_EPI_WARP0 + 3) * 32;               // 736
 
@@ -80,12 +81,6 @@ __device__ __forceinline__ void tt_store_rows(__half* dst, int E, const float (&
     }
 }
 
-// producer-side wait: the TMA warps are never latency-critical (their stages are released a whole unit ahead), so they sleep between
-// polls instead of competing for issue slots with the softmax warps of their SM sub-partition
-__device__ __forceinline__ void tt_wait_relaxed(uint32_t bar, uint32_t parity) {
-    while (!ptx::mbar_try_wait(bar, parity)) __nanosleep(200);
-}
-
 __global__ void __launch_bounds__(TT_THREADS, 1)
 attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
                     const __grid_constant__ CUtensorMap tm_s64, const __grid_constant__ CUtensorMap tm_s16,
@@ -98,15 +93,14 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
     auto bar = [&](int slot) { return bar0 + 8u * (uint32_t)slot; };
     const uint32_t tmem_slot = bar0 + 8u * BAR_COUNT;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + p.off_bar + 8 * BAR_COUNT);
-    float* colred = reinterpret_cast<float*>(smem_gen + p.off_red);                  // [2 parities][2 groups][8 warps][32]
-    float* colfin = colred + 2 * TT_SM_GROUPS * TT_SM_WARPS * TT_QG;                  // [2 groups][8 warps][32]
-    float* lsum = colfin + TT_SM_GROUPS * TT_SM_WARPS * TT_QG;                        // [2][64] softmax denominators
+    float* colred = reinterpret_cast<float*>(smem_gen + p.off_red);                  // [2 groups][2 slots][8 warps][32]
+    float* colfin = colred + 2 * TT_SM_GROUPS * TT_SM_WARPS * TT_QG;                  // [2 groups][8 warps][64]
+    float* lsum = colfin + TT_SM_GROUPS * TT_SM_WARPS * TT_Q;                         // [2][64] softmax denominators
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const int units = p.B * p.nhead;
     const int s_cols = p.n_mt * TT_Q;                // TMEM columns of one S^T accumulator set
-    const int ngrp = p.P > TT_QG ? TT_SM_GROUPS : 1;  // softmax groups with live query columns (<= 32 queries: group 0 alone)
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm_q64); ptx::prefetch_tensormap(&tm_q16);
@@ -114,13 +108,13 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
         ptx::prefetch_tensormap(&tm_c64); ptx::prefetch_tensormap(&tm_c16);
         ptx::prefetch_tensormap(&tm_sv); ptx::prefetch_tensormap(&tm_cv);
     }
-    if (warp == 1) {
+    if (warp == TT_MMA_WARP) {
         if (lane == 0) {
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(bar(BAR_KF + i), 1); ptx::mbar_init(bar(BAR_KE + i), 1);
                 ptx::mbar_init(bar(BAR_VF + i), 1); ptx::mbar_init(bar(BAR_VE + i), 1);
-                ptx::mbar_init(bar(BAR_SF + i), 1); ptx::mbar_init(bar(BAR_SE + i), TT_SM_WARPS * ngrp);
-                ptx::mbar_init(bar(BAR_PF + i), TT_SM_WARPS * ngrp); ptx::mbar_init(bar(BAR_PE + i), 1);
+                ptx::mbar_init(bar(BAR_SF + i), 1); ptx::mbar_init(bar(BAR_SE + i), TT_SM_WARPS);       // buffer i belongs to softmax group i
+                ptx::mbar_init(bar(BAR_PF + i), TT_SM_WARPS); ptx::mbar_init(bar(BAR_PE + i), 1);
                 ptx::mbar_init(bar(BAR_OF + i), 1); ptx::mbar_init(bar(BAR_OE + i), 3);
             }
             ptx::fence_barrier_init();
@@ -143,13 +137,13 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
 
     if (warp == 0) {
         // ===================== TMA producer: K and Q of a unit =====================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int uc = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
                 const int b = u / p.nhead, h = u - b * p.nhead;
                 const int slot = p.kv_slot ? p.kv_slot[b] : b;
                 const int st = uc % p.nk_st;
-                tt_wait_relaxed(bar(BAR_KE + st), (((uint32_t)(uc / p.nk_st)) & 1u) ^ 1u);
+                ptx::mbar_wait_hint(bar(BAR_KE + st), (((uint32_t)(uc / p.nk_st)) & 1u) ^ 1u);
                 const uint32_t fb = bar(BAR_KF + st);
                 trace_ev(p.trace, TR_TMA, TE_K_ISSUE, uc);
                 ptx::mbar_arrive_expect_tx(fb, (uint32_t)(p.self_rows + p.sbox + TT_Q) * 160u);
@@ -167,13 +161,13 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
         }
     } else if (warp == 2) {
         // ===================== TMA producer: V of a unit, as three 32-column boxes (the third runs past the head: see header) ======
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int uc = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
                 const int b = u / p.nhead, h = u - b * p.nhead;
                 const int slot = p.kv_slot ? p.kv_slot[b] : b;
                 const int st = uc % p.nv_st;
-                tt_wait_relaxed(bar(BAR_VE + st), (((uint32_t)(uc / p.nv_st)) & 1u) ^ 1u);
+                ptx::mbar_wait_hint(bar(BAR_VE + st), (((uint32_t)(uc / p.nv_st)) & 1u) ^ 1u);
                 const uint32_t fb = bar(BAR_VF + st);
                 trace_ev(p.trace, TR_TMAV, TE_V_ISSUE, uc);
                 ptx::mbar_arrive_expect_tx(fb, (uint32_t)(p.self_rows + p.sbox) * 192u);
@@ -186,17 +180,17 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == TT_MMA_WARP) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc1 = ptx::umma_idesc_f16_major(128, TT_Q, 0, 0);
         constexpr uint32_t idesc2 = ptx::umma_idesc_f16_major(128, TT_Q, 1, 1);
         auto issue_s = [&](int uc) {
             const int st = uc % p.nk_st, sb = uc & 1;
-            ptx::mbar_wait(bar(BAR_KF + st), ((uint32_t)(uc / p.nk_st)) & 1u);
+            ptx::mbar_wait_hint(bar(BAR_KF + st), ((uint32_t)(uc / p.nk_st)) & 1u);
             if (lane == 0) trace_ev(p.trace, TR_MMA, TE_K_READY, uc);
-            ptx::mbar_wait(bar(BAR_SE + sb), (((uint32_t)(uc >> 1)) & 1u) ^ 1u);
+            ptx::mbar_wait_hint(bar(BAR_SE + sb), (((uint32_t)(uc >> 1)) & 1u) ^ 1u);
             ptx::tc_fence_after();
-            if (lane == 0) {
+            if (ptx::elect_one()) {
                 const uint32_t base = k_stage(st);
                 for (int mt = 0; mt < p.n_mt; ++mt) {
                     const uint32_t d = tmem_base + (uint32_t)(sb * s_cols + mt * TT_Q);
@@ -220,12 +214,21 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
             const int slot = p.kv_slot ? p.kv_slot[b] : b;
             const int nk = p.self_rows + (p.kv_len ? p.kv_len[slot] : p.S_max);
             const int nks = (nk + 15) >> 4;
-            ptx::mbar_wait(bar(BAR_VF + st), ((uint32_t)(uc / p.nv_st)) & 1u);
-            ptx::mbar_wait(bar(BAR_PF + pb), ((uint32_t)(uc / p.npb)) & 1u);
+            ptx::mbar_wait_hint(bar(BAR_VF + st), ((uint32_t)(uc / p.nv_st)) & 1u);
+            // the V tile has landed: head-dim slot 80 of every key row := 1 (81..87 := 0), so that row 80 of O^T becomes the softmax
+            // denominator (third atom = head dims 64..95, 64-byte rows: slot 80 is 16-byte chunk 2, swizzled with address bits 7..8).
+            // Done HERE, by the otherwise idle lanes of the issuing warp, so the softmax groups never wait for a V load.
+            for (int r = lane; r < nks * 16; r += 32) {
+                uint8_t* vrow = smem_gen + p.off_v + (size_t)st * p.v_bytes + 2 * v_atom + (size_t)r * 64;
+                *reinterpret_cast<uint4*>(vrow + ((2 ^ ((r >> 1) & 3)) << 4)) = make_uint4(0x00003C00u, 0u, 0u, 0u);
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            ptx::mbar_wait_hint(bar(BAR_PF + pb), ((uint32_t)(uc / p.npb)) & 1u);
             if (lane == 0) trace_ev(p.trace, TR_MMA, TE_P_READY, uc);
-            ptx::mbar_wait(bar(BAR_OE + ob), (((uint32_t)(uc >> 1)) & 1u) ^ 1u);
+            ptx::mbar_wait_hint(bar(BAR_OE + ob), (((uint32_t)(uc >> 1)) & 1u) ^ 1u);
             ptx::tc_fence_after();
-            if (lane == 0) {
+            if (ptx::elect_one()) {
                 const uint32_t va = v_stage(st);
                 const uint32_t pt = smem_base + p.off_p + (uint32_t)pb * p.p_bytes;
                 const uint32_t d = tmem_base + col_o + (uint32_t)(ob * TT_Q);
@@ -239,88 +242,100 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
             }
             __syncwarp();
         };
+        // Unit uc's softmax group frees S^T buffer uc&1 and delivers P^T(uc) at the same moment: S^T(uc+2) -- what that group
+        // waits for next -- goes to the tensor pipe FIRST, MMA2(uc) behind it (its consumer, the epilogue, has a spare O^T buffer).
+        // Both cost ~1 300 cycles here (operand reads at the shared-memory port's limit), so the order is worth one of them
+        // per unit on the group's critical path (in-kernel timeline, profiles/r02m_trace_attention_tt.txt).
         int uc = 0, u = blockIdx.x;
         if (u < units) issue_s(0);
+        if (u + (int)gridDim.x < units) issue_s(1);
         for (; u < units; u += gridDim.x, ++uc) {
-            if (u + (int)gridDim.x < units) issue_s(uc + 1);          // S^T of the next unit overlaps this unit's softmax
+            if (u + 2 * (int)gridDim.x < units) issue_s(uc + 2);
             issue_o(uc, u);
         }
     } else if (warp >= 4 && warp < TT_EPI_WARP0) {
         // ===================== softmax down the lanes: S^T (TMEM) -> P^T (shared, fp16, MN-major 128B swizzle) =====================
-        // two groups of 8 warps split the 64 query columns; inside a group warp sw owns key tile sw/4, TMEM sub-partition sw%4
-        // (with <= 32 queries the second group has no live column: its warps go straight to the final barrier, and the columns
-        //  32..63 of P^T / O^T hold garbage nobody reads -- an accumulator column depends on its own B column only)
+        // Two groups of 8 warps take ALTERNATE units (group g: units g, g+2, ... of this CTA = S^T / P^T buffer g), each all 64
+        // query columns in two 32-column halves; inside a group warp sw owns key tile sw/4, TMEM sub-partition sw%4.  The groups
+        // run half a period apart, so on every SM sub-partition one group's transpose-reduce / exp2 stream fills the other's
+        // TMEM-load, shuffle and barrier latencies (the earlier split -- both groups on the SAME unit, 32 columns each -- left all
+        // 16 warps stalling in phase: 50 % issue utilisation in ncu, profiles/r02i_*).
         const int grp = (warp - 4) >> 3;
         const int sw = (warp - 4) & 7;
         const int mt = sw >> 2;
         const int j = mt * 128 + (warp & 3) * 32 + lane;             // this thread's key row
         const bool tile_here = mt < p.n_mt;
         const int bar_id = 1 + grp;
-        float* fin = colfin + (grp * TT_SM_WARPS + sw) * TT_QG;
-        int uc = 0;
-        for (int u = grp < ngrp ? blockIdx.x : units; u < units; u += gridDim.x, ++uc) {
+        const int nhalf = p.P > 32 ? 2 : 1;                          // 32-query halves with live columns
+        float* fin = colfin + (grp * TT_SM_WARPS + sw) * TT_Q;       // this warp's copy of the 64 column maxima (x scale)
+        uint32_t syncs = 0;                                          // named-barrier rounds of this group: selects the exchange slot
+        const int sb = grp, pb = grp;                                // unit parity = group: it owns these buffers
+        for (int u = blockIdx.x + grp * gridDim.x, uc = grp; u < units; u += 2 * gridDim.x, uc += 2) {
             const int b = u / p.nhead;
             const int slot = p.kv_slot ? p.kv_slot[b] : b;
             const int nk = p.self_rows + (p.kv_len ? p.kv_len[slot] : p.S_max);
             const int nk16 = (nk + 15) & ~15;
-            const int sb = uc & 1, pb = uc % p.npb, vst = uc % p.nv_st;
             const bool tr = sw == 0 && lane == 0;
-            const uint32_t ts = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(sb * s_cols + mt * TT_Q + grp * TT_QG);
+            const uint32_t ts = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(sb * s_cols + mt * TT_Q);
+            const uint32_t par = ((uint32_t)(uc >> 1)) & 1u;
+            const bool live = tile_here && j < nk;
+            const bool all_live = tile_here && ((j | 31) < nk);      // warp-uniform: no row of this warp needs masking
             float v[32];
-            ptx::mbar_wait(bar(BAR_SF + sb), ((uint32_t)(uc >> 1)) & 1u);
+            ptx::mbar_wait_hint(bar(BAR_SF + sb), par);
             if (tr) trace_ev(p.trace, TR_SM + grp, TE_S_READY, uc);
             ptx::tc_fence_after();
-            const bool live = tile_here && j < nk;
-            if (tile_here) ptx::tmem_ld_32x32(ts, v);                 // warp-collective: never under a per-lane condition
+            for (int hf = 0; hf < nhalf; ++hf) {
+                if (tile_here) ptx::tmem_ld_32x32(ts + (uint32_t)(hf * 32), v);      // warp-collective: never under a per-lane condition
+                if (!all_live) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = live ? v[i] : -INFINITY;
-            // column maxima over this warp's 32 key rows: each round halves the column set a lane holds and exchanges the other
-            // half with lane ^ mask; after five rounds lane l holds column l
+                    for (int i = 0; i < 32; ++i) v[i] = live ? v[i] : -INFINITY;
+                }
+                // column maxima over this warp's 32 key rows: each round halves the column set a lane holds and exchanges the
+                // other half with lane ^ mask; after five rounds lane l holds column l
 #define TT_MAX_ROUND(W, MASK)                                                                       \
     _Pragma("unroll") for (int i = 0; i < (W); ++i) {                                                \
         const bool up = (lane & (MASK)) != 0;                                                        \
         const float send = up ? v[i] : v[i + (W)], keep = up ? v[i + (W)] : v[i];                    \
         v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, (MASK)));                              \
     }
-            TT_MAX_ROUND(16, 16) TT_MAX_ROUND(8, 8) TT_MAX_ROUND(4, 4) TT_MAX_ROUND(2, 2) TT_MAX_ROUND(1, 1)
+                TT_MAX_ROUND(16, 16) TT_MAX_ROUND(8, 8) TT_MAX_ROUND(4, 4) TT_MAX_ROUND(2, 2) TT_MAX_ROUND(1, 1)
 #undef TT_MAX_ROUND
-            float* red = colred + ((uc & 1) * TT_SM_GROUPS + grp) * (TT_SM_WARPS * TT_QG);
-            red[sw * TT_QG + lane] = v[0];
-            ptx::bar_sync(bar_id, TT_SM_WARPS * 32);
-            float mx = v[0];
+                // exchange between the group's 8 warps: two slots, alternating per barrier round (a slot is rewritten two rounds
+                // later, after every warp has passed the round in between, i.e. finished reading it)
+                float* red = colred + (grp * 2 + (int)(syncs & 1u)) * (TT_SM_WARPS * TT_QG);
+                ++syncs;
+                red[sw * TT_QG + lane] = v[0];
+                ptx::bar_sync(bar_id, TT_SM_WARPS * 32);
+                float mx = v[0];
 #pragma unroll
-            for (int w = 0; w < TT_SM_WARPS; ++w) mx = fmaxf(mx, red[w * TT_QG + lane]);
-            __syncwarp();                               // this warp's reads of `fin` for the previous unit are done
-            fin[lane] = mx * p.scale_log2;
+                for (int w = 0; w < TT_SM_WARPS; ++w) mx = fmaxf(mx, red[w * TT_QG + lane]);
+                if (hf == 0) __syncwarp();              // this warp's reads of `fin` for its previous unit are done
+                fin[hf * TT_QG + lane] = mx * p.scale_log2;
+            }
             __syncwarp();
             if (tr) trace_ev(p.trace, TR_SM + grp, TE_MAX_DONE, uc);
-            ptx::mbar_wait(bar(BAR_PE + pb), (((uint32_t)(uc / p.npb)) & 1u) ^ 1u);       // the P^T buffer is free again
-            if (grp == 0) ptx::mbar_wait(bar(BAR_VF + vst), ((uint32_t)(uc / p.nv_st)) & 1u);   // the V tile has landed (ones column below)
+            ptx::mbar_wait_hint(bar(BAR_PE + pb), par ^ 1u);               // this group's P^T buffer is free again (MMA2 of unit uc-2)
             if (tr) trace_ev(p.trace, TR_SM + grp, TE_P_FREE, uc);
-            if (tile_here) ptx::tmem_ld_32x32(ts, v);                 // the reduce ran in place: re-read the scores (warp-collective)
-            if (tile_here && j < nk16) {
-                uint8_t* prow = smem_gen + p.off_p + (size_t)pb * p.p_bytes + (size_t)j * 128;
-                const float4* mf = reinterpret_cast<const float4*>(fin);
+            for (int hf = 0; hf < nhalf; ++hf) {
+                if (tile_here) ptx::tmem_ld_32x32(ts + (uint32_t)(hf * 32), v);      // the reduce ran in place: re-read the scores
+                if (tile_here && j < nk16) {
+                    uint8_t* prow = smem_gen + p.off_p + (size_t)pb * p.p_bytes + (size_t)j * 128;
+                    const float4* mf = reinterpret_cast<const float4*>(fin + hf * TT_QG);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {           // 16-byte chunk 4*grp + c = queries 32*grp + 8c .. + 7
-                    const float4 m0 = mf[2 * c], m1 = mf[2 * c + 1];
-                    uint4 pk;
-                    pk.x = pack_half2(ptx::ex2_approx(fmaf(v[8 * c + 0], p.scale_log2, -m0.x)), ptx::ex2_approx(fmaf(v[8 * c + 1], p.scale_log2, -m0.y)));
-                    pk.y = pack_half2(ptx::ex2_approx(fmaf(v[8 * c + 2], p.scale_log2, -m0.z)), ptx::ex2_approx(fmaf(v[8 * c + 3], p.scale_log2, -m0.w)));
-                    pk.z = pack_half2(ptx::ex2_approx(fmaf(v[8 * c + 4], p.scale_log2, -m1.x)), ptx::ex2_approx(fmaf(v[8 * c + 5], p.scale_log2, -m1.y)));
-                    pk.w = pack_half2(ptx::ex2_approx(fmaf(v[8 * c + 6], p.scale_log2, -m1.z)), ptx::ex2_approx(fmaf(v[8 * c + 7], p.scale_log2, -m1.w)));
-                    if (!live) pk = make_uint4(0u, 0u, 0u, 0u);          // padding key rows up to the MMA's K step: P^T = 0
-                    *reinterpret_cast<uint4*>(prow + (((4 * grp + c) ^ (j & 7)) << 4)) = pk;
-                }
-                if (grp == 0) {
-                    // head-dim slot 80 of this key's V row := 1 (81..87 := 0): row 80 of O^T becomes the softmax denominator
-                    // (third atom = head dims 64..95, 64-byte rows: slot 80 is 16-byte chunk 2, swizzled with address bits 7..8)
-                    uint8_t* vrow = smem_gen + p.off_v + (size_t)vst * p.v_bytes + 2 * v_atom + (size_t)j * 64;
-                    *reinterpret_cast<uint4*>(vrow + ((2 ^ ((j >> 1) & 3)) << 4)) = make_uint4(0x00003C00u, 0u, 0u, 0u);
+                    for (int c = 0; c < 4; ++c) {           // 16-byte chunk 4*hf + c = queries 32*hf + 8c .. + 7
+                        const float4 m0 = mf[2 * c], m1 = mf[2 * c + 1];
+                        uint4 pk;
+                        pk.x = pack_half2(ptx::ex2_approx(fmaf(v[8 * c + 0], p.scale_log2, -m0.x)), ptx::ex2_approx(fmaf(v[8 * c + 1], p.scale_log2, -m0.y)));
+                        pk.y = pack_half2(ptx::ex2_approx(fmaf(v[8 * c + 2], p.scale_log2, -m0.z)), ptx::ex2_approx(fmaf(v[8 * c + 3], p.scale_log2, -m0.w)));
+                        pk.z = pack_half2(ptx::ex2_approx(fmaf(v[8 * c + 4], p.scale_log2, -m1.x)), ptx::ex2_approx(fmaf(v[8 * c + 5], p.scale_log2, -m1.y)));
+                        pk.w = pack_half2(ptx::ex2_approx(fmaf(v[8 * c + 6], p.scale_log2, -m1.z)), ptx::ex2_approx(fmaf(v[8 * c + 7], p.scale_log2, -m1.w)));
+                        if (!live) pk = make_uint4(0u, 0u, 0u, 0u);          // padding key rows up to the MMA's K step: P^T = 0
+                        *reinterpret_cast<uint4*>(prow + (((4 * hf + c) ^ (j & 7)) << 4)) = pk;
+                    }
                 }
             }
             ptx::tc_fence_before();
-            ptx::fence_proxy_async_smem();              // generic-proxy stores (P^T, the ones) -> visible to the tensor core
+            ptx::fence_proxy_async_smem();              // generic-proxy stores (P^T) -> visible to the tensor core
             __syncwarp();
             if (lane == 0) {
                 ptx::mbar_arrive(bar(BAR_SE + sb));
@@ -337,7 +352,7 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
         for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
             const int b = u / p.nhead, h = u - b * p.nhead;
             const int ob = uc & 1;
-            ptx::mbar_wait(bar(BAR_OF + ob), ((uint32_t)(uc >> 1)) & 1u);
+            ptx::mbar_wait_hint(bar(BAR_OF + ob), ((uint32_t)(uc >> 1)) & 1u);
             if (wq == 0 && lane == 0) trace_ev(p.trace, TR_EPI, TE_O_READY, uc);
             ptx::tc_fence_after();
             const uint32_t to = tmem_base + ((uint32_t)(wq * 32) << 16) + col_o + (uint32_t)(ob * TT_Q);
@@ -380,7 +395,7 @@ attention_tt_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+    if (warp == TT_MMA_WARP) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 int tt_tmap(const void* ptr, int64_t rows, int64_t cols, int box_cols, int box_rows, CUtensorMap* out) {
@@ -409,17 +424,13 @@ int launch_attention_tt(const AttnParams& a, cudaStream_t st) {
     p.k_bytes = ((uint32_t)(TT_Q * 160 + p.n1 * 160) + 1023u) & ~1023u;
     p.v_bytes = (uint32_t)p.n1 * 192u;
     p.p_bytes = (uint32_t)p.n1 * 128u;
-    const uint32_t red_bytes = (2 * TT_SM_GROUPS * TT_SM_WARPS * TT_QG + TT_SM_GROUPS * TT_SM_WARPS * TT_QG + 2 * TT_Q) * 4;
+    const uint32_t red_bytes = (2 * TT_SM_GROUPS * TT_SM_WARPS * TT_QG + TT_SM_GROUPS * TT_SM_WARPS * TT_Q + 2 * TT_Q) * 4;
     // MMA1 reads whole 128-row key tiles (the rows past n1 are masked by the softmax) and MMA2 a fourth V atom (rows nobody
     // reads): whatever follows in shared memory.  K stages first, then V, then P^T: every over-read stays inside the allocation
     const uint32_t fixed = red_bytes + 8 * (BAR_COUNT + 1) + 1024 /*alignment slack*/;
     const uint32_t cap = 227 * 1024;
-    p.nk_st = 2; p.nv_st = 2; p.npb = 2;
-    auto total = [&]() { return fixed + p.nk_st * p.k_bytes + p.nv_st * p.v_bytes + p.npb * p.p_bytes; };
-    if (total() > cap) p.npb = 1;
-    if (total() > cap) p.nv_st = 1;
-    if (total() > cap) p.nk_st = 1;
-    if (total() > cap) return -1;
+    p.nk_st = 2; p.nv_st = 2; p.npb = 2;      // softmax group g owns stage g of every ring: all rings are two deep
+    if (fixed + p.nk_st * p.k_bytes + p.nv_st * p.v_bytes + p.npb * p.p_bytes > cap) return -1;      // more keys: attention_tc
     p.off_k = 0;
     p.off_v = p.nk_st * p.k_bytes;
     p.off_p = p.off_v + p.nv_st * p.v_bytes;

@@ -48,6 +48,42 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// Same with a suspend-time hint on try_wait (the form CUTLASS's ClusterBarrier::wait uses, 0x989680 ticks): the warp sleeps in
+// hardware until the phase flips instead of re-issuing the poll -- for kernels whose waiting roles share an SM sub-partition with
+// busy compute warps (attention_tt.cu: the polls of the MMA / TMA warps cost the softmax warps beside them issue slots).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ticks) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(ticks)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, 0x989680u)) {
+        if ((++spins & 0x3f) == 0 && globaltimer_ns() - t0 > 4000000000ull) {   // 4 s
+            printf("paella_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+
+// One elected lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows the guarded region runs in exactly one
+// thread, so single-thread instructions (tcgen05.mma / commit, TMA) are emitted straight instead of inside an ELECT / BRA.U.ANY
+// "uniformisation" loop each.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------ thread-block clusters
 __device__ __forceinline__ uint32_t cluster_nctarank() {
     uint32_t v;
