@@ -125,7 +125,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
 
     if (warp == 0) {
         // ===================== TMA producer: K tiles (per unit) and Q tiles (per query tile) =====================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int it = 0, uc = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
                 const int b = u / p.nhead, h = u - b * p.nhead;
@@ -155,7 +155,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
         }
     } else if (warp == 2) {
         // ===================== TMA producer: V tiles (their stage frees much later than K's: own thread, own barriers) =====================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int uc = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
                 const int b = u / p.nhead, h = u - b * p.nhead;
@@ -201,7 +201,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
             ptx::mbar_wait(bar(BAR_QF + qs), ((uint32_t)(c.it >> 1)) & 1u);
             ptx::mbar_wait(bar(BAR_SE + sb), (((uint32_t)(c.it / p.nsb)) & 1u) ^ 1u);
             ptx::tc_fence_after();
-            if (lane == 0) {
+            if (ptx::elect_one()) {
                 const uint32_t k64 = kv_stage(st), k16 = k64 + 2 * p.k64_bytes;
                 const uint32_t d = tmem_base + (uint32_t)(sb * p.n1);
 #pragma unroll
@@ -233,7 +233,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_con
             if (lane == 0) trace_ev(p.trace, TR_MMA, TE_P_READY, c.it);
             ptx::mbar_wait(bar(BAR_OE), (((uint32_t)c.it) & 1u) ^ 1u);
             ptx::tc_fence_after();
-            if (lane == 0) {
+            if (ptx::elect_one()) {
                 const uint32_t v64 = kv_stage(st) + p.k64_bytes, v16 = v64 + p.k64_bytes + p.k16_bytes;
                 const uint32_t pt = smem_base + p.off_p + (uint32_t)pb * p.p_bytes;
                 const uint32_t d = tmem_base + col_o;

@@ -503,7 +503,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
@@ -566,7 +566,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             for (int kb = 0; kb < n_kb; ++kb) {
                 ptx::mbar_wait(full_bar(stage), phase);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                if (ptx::elect_one()) {
                     const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
                     const uint64_t da = ptx::umma_desc_kmajor_sw128(sa);
                     const uint64_t db = ptx::umma_desc_kmajor_sw128(sa + L::A_BYTES);
@@ -742,7 +742,7 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t leader_full0 = ptx::mapa(full_bar(0), 0);      // leader's full[0] in cluster address space
@@ -794,7 +794,7 @@ gemm_f16_cg2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     ptx::mbar_wait(full_bar(stage), phase);
                     if (ASCALE) ptx::mbar_wait(ready_bar(stage), phase);
                     ptx::tc_fence_after();
-                    if (lane == 0) {
+                    if (ptx::elect_one()) {
                         const uint32_t sa = smem_base + stage * STAGE_BYTES;
                         const uint64_t da = ptx::umma_desc_kmajor_sw128(sa);
                         const uint64_t db = ptx::umma_desc_kmajor_sw128(sa + A_BYTES);

@@ -76,7 +76,7 @@ fused_sampler_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(a_bar, n_kb * SMP_A_BYTES);
             for (int kb = 0; kb < n_kb; ++kb) ptx::tma_load_2d(&tm_a, a_bar, a_base + kb * SMP_A_BYTES, kb * 64, m_idx);
             int stage = 0;
@@ -101,7 +101,7 @@ fused_sampler_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             for (int kb = 0; kb < n_kb; ++kb) {
                 ptx::mbar_wait(full_bar(stage), phase);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                if (ptx::elect_one()) {
                     const uint64_t da = ptx::umma_desc_kmajor_sw128(a_base + kb * SMP_A_BYTES);
                     const uint64_t db = ptx::umma_desc_kmajor_sw128(w_base + stage * SMP_W_BYTES);
 #pragma unroll
@@ -254,7 +254,7 @@ fused_sampler_shared_kernel(const __grid_constant__ CUtensorMap tm_f, const __gr
     const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(f_bar, n_kb * SH_F_BYTES);
             for (int kb = 0; kb < n_kb; ++kb) ptx::tma_load_4d(&tm_f, f_bar, f_base + kb * SH_F_BYTES, kb * 64, 0, jj0, blk);
             int stage = 0;
@@ -279,7 +279,7 @@ fused_sampler_shared_kernel(const __grid_constant__ CUtensorMap tm_f, const __gr
             for (int kb = 0; kb < n_kb; ++kb) {
                 ptx::mbar_wait(full_bar(stage), phase);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                if (ptx::elect_one()) {
                     const uint64_t da = ptx::umma_desc_kmajor_sw128(w_base + stage * SH_W_BYTES);     // labels = M
                     const uint64_t db = ptx::umma_desc_kmajor_sw128(f_base + kb * SH_F_BYTES);        // tokens = N
 #pragma unroll

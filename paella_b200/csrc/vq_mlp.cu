@@ -124,7 +124,7 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs): A once per tile, W1 k-blocks and W2 chunks as rings =====================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             const uint32_t l_a_full = ptx::mapa(a_full, 0), l_w1_full0 = ptx::mapa(w1_full0, 0), l_w2_full0 = ptx::mapa(w2_full0, 0);
             int s1 = 0, s2 = 0;
             uint32_t p1 = 0, p2 = 0, pa = 0;
@@ -178,7 +178,7 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     ptx::mbar_wait(w1_full0 + 8u * s1, p1);
                     if (kb == 0 && lane == 0) trace_ev(trace, MR_MMA, ME_G1_GO, c1);
                     ptx::tc_fence_after();
-                    if (lane == 0) {
+                    if (ptx::elect_one()) {
                         const uint64_t da = ptx::umma_desc_kmajor_sw128(sA + kb * 16384);
                         const uint64_t db = ptx::umma_desc_kmajor_sw128(sW1 + s1 * L::W1_STAGE);
 #pragma unroll
@@ -201,7 +201,7 @@ vq_mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 ptx::mbar_wait(w2_full0 + 8u * s2, p2);
                 if (first) ptx::mbar_wait(acc2_empty, (((uint32_t)tiles_done) & 1u) ^ 1u);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                if (ptx::elect_one()) {
                     trace_ev(trace, MR_MMA, ME_G2_GO, c2);
                     const uint64_t da = ptx::umma_desc_kmajor_sw128(sH + hb * L::H_BYTES);
                     const uint64_t dba = ptx::umma_desc_kmajor_sw128(sW2 + s2 * L::W2_STAGE);
