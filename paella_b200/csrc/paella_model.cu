@@ -539,6 +539,7 @@ int pb200_paella_load_param(pb200_paella* m, const char* name, const float* src,
 }
 
 int64_t pb200_paella_workspace_bytes(const pb200_paella* m, int batch_total, int h, int w, int s_max) {
+    if (m == nullptr) { set_error("workspace_bytes: null model handle"); return -1; }
     Arena a{nullptr};
     FeatWs f;
     plan_features(m, batch_total, h, w, a, f);
@@ -555,6 +556,7 @@ int64_t pb200_paella_workspace_bytes(const pb200_paella* m, int batch_total, int
 }
 
 int64_t pb200_paella_cond_cache_bytes(const pb200_paella* m, int batch_total, int s_max) {
+    if (m == nullptr) { set_error("cond_cache_bytes: null model handle"); return -1; }
     return cond_block_off(m, m->n_attn, batch_total, s_max) + ((int64_t)batch_total * 4 + 255) / 256 * 256;
 }
 

@@ -60,33 +60,49 @@ __global__ void vq_pack_kernel(const float* __restrict__ src, void* __restrict__
 }
 
 // ------------------------------------------------------------------ image-side / latent-side 1x1 convs (CUDA cores)
-// in_block: PixelUnshuffle(2) + Conv2d(12 -> c0, k=1).  img NCHW [B,3,H,W] -> NHWC fp32 [B,H/2,W/2,c0]
-__global__ void __launch_bounds__(256) vq_in_block_kernel(const float* __restrict__ img, const float* __restrict__ w,
-                                                          const float* __restrict__ bias, int B, int H, int W, int c0,
-                                                          float* __restrict__ out) {
+// in_block: PixelUnshuffle(2) + Conv2d(12 -> c0, k=1).  img NCHW [B,3,H,W] -> NHWC fp32 [B,H/2,W/2,c0].  w is packed [12][c0]
+// (VP_T12): one coalesced float4 per input tap and channel quad.  Round 2 history: [c0][12] weights (48 loads per thread, each
+// touching 32 lines per warp) took 4.7 ms for 64 images; a thread per (position, quad) with 12 scalar image loads + 12 weight
+// loads per 48 FMA sat at 1.5 TB/s (ncu: L1 73 %); now:
+// in_block, register-resident weights: a thread keeps the 12 x 4 weights of ITS channel quad and walks VQ_IN_PPT consecutive
+// positions of a row (two 2-pixel-wide float2 loads per plane and position instead of 12 scalar loads + 12 weight loads)
+constexpr int VQ_IN_PPT = 4;
+__global__ void __launch_bounds__(192) vq_in_block_rw_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, int B, int H, int W, int c0,
+                                                             float* __restrict__ out) {
     const int h2 = H >> 1, w2 = W >> 1, nq = c0 >> 2;
+    const int groups_x = (w2 + VQ_IN_PPT - 1) / VQ_IN_PPT;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * h2 * w2 * nq) return;
+    if (i >= (int64_t)B * h2 * groups_x * nq) return;
     const int q = (int)(i % nq);
-    const int64_t pos = i / nq;
-    const int b = (int)(pos / ((int64_t)h2 * w2));
-    const int rem = (int)(pos - (int64_t)b * h2 * w2);
-    const int y = rem / w2, x = rem - y * w2;
-    float in[12];
+    const int64_t grp = i / nq;
+    const int gx = (int)(grp % groups_x);
+    const int64_t row = grp / groups_x;                 // b * h2 + y
+    const int b = (int)(row / h2), y = (int)(row - (int64_t)b * h2);
+    float4 wv[12];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+    for (int k = 0; k < 12; ++k) wv[k] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)k * c0) + q);
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + q);
 #pragma unroll
-        for (int d = 0; d < 4; ++d)
-            in[c * 4 + d] = img[(((int64_t)b * 3 + c) * H + 2 * y + (d >> 1)) * W + 2 * x + (d & 1)];
-    // w is packed [12][c0] (VP_T12): one coalesced float4 per input tap (round 2 first had [c0][12]: 48 loads per thread,
-    // each touching 32 different lines per warp -- 4.7 ms for 64 images, 35x the time of the 805 MB store it feeds)
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + q);
+    for (int pi = 0; pi < VQ_IN_PPT; ++pi) {
+        const int x = gx * VQ_IN_PPT + pi;
+        if (x >= w2) break;
+        float in[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-        const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (int64_t)k * c0) + q);
-        acc.x = fmaf(in[k], ww.x, acc.x); acc.y = fmaf(in[k], ww.y, acc.y); acc.z = fmaf(in[k], ww.z, acc.z); acc.w = fmaf(in[k], ww.w, acc.w);
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const float2 v = *reinterpret_cast<const float2*>(img + (((int64_t)b * 3 + c) * H + 2 * y + dy) * W + 2 * x);
+                in[c * 4 + dy * 2] = v.x; in[c * 4 + dy * 2 + 1] = v.y;
+            }
+        float4 acc = bv;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            acc.x = fmaf(in[k], wv[k].x, acc.x); acc.y = fmaf(in[k], wv[k].y, acc.y);
+            acc.z = fmaf(in[k], wv[k].z, acc.z); acc.w = fmaf(in[k], wv[k].w, acc.w);
+        }
+        *reinterpret_cast<float4*>(out + ((row * w2) + x) * c0 + q * 4) = acc;
     }
-    *reinterpret_cast<float4*>(out + pos * c0 + q * 4) = acc;
 }
 
 // out_block: Conv2d(c0 -> 12, k=1) + PixelShuffle(2).  x NHWC fp32 [B,h2,w2,c0] -> img NCHW [B,3,2h2,2w2]; warp per position.
@@ -118,6 +134,59 @@ __global__ void __launch_bounds__(256) vq_out_block_kernel(const float* __restri
         const int y = rem / w2, xx = rem - y * w2;
         const int c = lane >> 2, d = lane & 3;
         v += bias[lane];
+        if (MODE != 0) v = fminf(fmaxf(v, 0.f), 1.f);
+        if (MODE == 2) {
+            uint8_t* img = reinterpret_cast<uint8_t*>(img_out);
+            img[(((int64_t)b * (2 * h2) + 2 * y + (d >> 1)) * (2 * w2) + 2 * xx + (d & 1)) * 3 + c] =
+                (uint8_t)fminf(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f), 255.0f);      // mul then add, two roundings like the torch ops (no FMA)
+        } else {
+            float* img = reinterpret_cast<float*>(img_out);
+            img[(((int64_t)b * 3 + c) * (2 * h2) + 2 * y + (d >> 1)) * (2 * w2) + 2 * xx + (d & 1)] = v;
+        }
+    }
+}
+
+// out_block, thread per position (c0 % 32 == 0): the warp-per-position kernel above issues 72 weight loads and 60 shuffles per
+// lane and position (ncu: LSU 63 %, 0.96 TB/s).  Here a thread owns a position: it pulls its row in 128-byte pieces (eight 16-byte
+// loads, consumed at once) and multiplies against the 12 x c0 weights staged in shared memory as [c/4][12] float4 (warp-wide
+// broadcast reads) -- 1.5 global loads + 18 shared loads per 72 FFMA.  Summation order: channels ascending per output.
+template <int MODE>
+__global__ void __launch_bounds__(128) vq_out_block_tp_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, int B, int h2, int w2, int c0,
+                                                              void* __restrict__ img_out) {
+    extern __shared__ float4 w_s[];                      // [c0/4][12]: the 4 channel weights of output o
+    const int nj = c0 >> 2;
+    for (int i = threadIdx.x; i < nj * 12; i += blockDim.x) {
+        const int j = i / 12, o = i - j * 12;
+        w_s[i] = *reinterpret_cast<const float4*>(w + (int64_t)o * c0 + 4 * j);
+    }
+    __syncthreads();
+    const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= (int64_t)B * h2 * w2) return;
+    float acc[12];
+#pragma unroll
+    for (int o = 0; o < 12; ++o) acc[o] = __ldg(bias + o);
+    const float4* xr = reinterpret_cast<const float4*>(x + pos * c0);
+    for (int j0 = 0; j0 < nj; j0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = xr[j0 + t];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+#pragma unroll
+            for (int o = 0; o < 12; ++o) {
+                const float4 ww = w_s[(j0 + t) * 12 + o];
+                acc[o] = fmaf(v[t].w, ww.w, fmaf(v[t].z, ww.z, fmaf(v[t].y, ww.y, fmaf(v[t].x, ww.x, acc[o]))));
+            }
+        }
+    }
+    const int b = (int)(pos / ((int64_t)h2 * w2));
+    const int rem = (int)(pos - (int64_t)b * h2 * w2);
+    const int y = rem / w2, xx = rem - y * w2;
+#pragma unroll
+    for (int o = 0; o < 12; ++o) {
+        float v = acc[o];
+        const int c = o >> 2, d = o & 3;
         if (MODE != 0) v = fminf(fmaxf(v, 0.f), 1.f);
         if (MODE == 2) {
             uint8_t* img = reinterpret_cast<uint8_t*>(img_out);
@@ -181,6 +250,24 @@ __global__ void __launch_bounds__(256) vq_dec_head_kernel(const float* __restric
         o[j] = acc;
     }
     *reinterpret_cast<float4*>(out + pos * c1 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// the same for cl == 4 (the f4 codec): z and each output channel's weights are ONE 16-byte load -- 5 loads per thread instead of
+// 40 (ncu, round 2: the scalar version sat at 63 % `lg_throttle` stalls, 213 us for a 100 MB store)
+__global__ void __launch_bounds__(256) vq_dec_head4_kernel(const float* __restrict__ z, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, int64_t M, int c1,
+                                                           float* __restrict__ out) {
+    const int nq = c1 >> 2;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * nq) return;
+    const int q = (int)(i % nq);
+    const int64_t pos = i / nq;
+    const float4 zv = *(reinterpret_cast<const float4*>(z) + pos);
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + q);
+    const float4* wr = reinterpret_cast<const float4*>(w) + q * 4;          // rows 4q .. 4q+3 of w [c1, 4]
+    const float4 w0 = __ldg(wr), w1 = __ldg(wr + 1), w2 = __ldg(wr + 2), w3 = __ldg(wr + 3);
+    auto dot = [&](float b, const float4& ww) { return fmaf(zv.w, ww.w, fmaf(zv.z, ww.z, fmaf(zv.y, ww.y, fmaf(zv.x, ww.x, b)))); };
+    *reinterpret_cast<float4*>(out + pos * c1 + q * 4) = make_float4(dot(bv.x, w0), dot(bv.y, w1), dot(bv.z, w2), dot(bv.w, w3));
 }
 
 // ResBlock middle: x += (depthwise3x3(ReplicationPad(xt)) + bias) * g2; xt, x NHWC fp32; w9 [9][c]
@@ -522,8 +609,9 @@ int pb200_vqgan_encode(pb200_vqgan* m, const float* img, int batch, int img_h, i
     const int64_t M0 = (int64_t)B * h0 * w0, M1 = (int64_t)B * h1 * w1;
     {
         ProfScope prof("vq_in_block", (double)M0 * (48.0 + c0 * 4.0), st);
-        vq_in_block_kernel<<<ceil_div(M0 * (c0 / 4), 256), 256, 0, st>>>(img, m->w<float>(m->in_w), m->w<float>(m->in_b), B, img_h,
-                                                                        img_w, c0, ws.xa);
+        const int64_t n_thr = (int64_t)B * h0 * ceil_div(w0, VQ_IN_PPT) * (c0 / 4);
+        vq_in_block_rw_kernel<<<ceil_div(n_thr, 192), 192, 0, st>>>(img, m->w<float>(m->in_w), m->w<float>(m->in_b), B, img_h, img_w,
+                                                                    c0, ws.xa);
         PB_LAUNCH_CHECK();
     }
     PB_TRY(run_resblock(m, m->enc0, ws.xa, B, h0, w0, ws, st));
@@ -593,8 +681,11 @@ int pb200_vqgan_decode_ex(pb200_vqgan* m, const int64_t* indices, const float* l
         PB_TRY(launch_nchw_to_nhwc(latents_nchw, B, cl, h1 * w1, ws.zq, st));
     {
         ProfScope prof("vq_dec_head", (double)M1 * c1 * 4.0, st);
-        vq_dec_head_kernel<<<ceil_div(M1 * (c1 / 4), 256), 256, 0, st>>>(ws.zq, m->w<float>(m->dec_w), m->w<float>(m->dec_b), M1, cl, c1,
-                                                                        ws.xb);
+        if (cl == 4)
+            vq_dec_head4_kernel<<<ceil_div(M1 * (c1 / 4), 256), 256, 0, st>>>(ws.zq, m->w<float>(m->dec_w), m->w<float>(m->dec_b), M1, c1, ws.xb);
+        else
+            vq_dec_head_kernel<<<ceil_div(M1 * (c1 / 4), 256), 256, 0, st>>>(ws.zq, m->w<float>(m->dec_w), m->w<float>(m->dec_b), M1, cl, c1,
+                                                                            ws.xb);
         PB_LAUNCH_CHECK();
     }
     for (const VqResBlock& rb : m->bottleneck) PB_TRY(run_resblock(m, rb, ws.xb, B, h1, w1, ws, st));
@@ -626,7 +717,13 @@ int pb200_vqgan_decode_ex(pb200_vqgan* m, const int64_t* indices, const float* l
     {
         ProfScope prof("vq_out_block", (double)M0 * (c0 * 4.0 + 48.0), st);
         const float *ow = m->w<float>(m->out_w), *ob = m->w<float>(m->out_b);
-        if (img_mode == PB200_IMG_U8_NHWC) vq_out_block_kernel<2><<<ceil_div(M0, 8), 256, 0, st>>>(ws.xa, ow, ob, B, h0, w0, c0, img);
+        if (c0 % 32 == 0 && c0 <= 768) {         // thread per position, weights in shared memory
+            const size_t sm = (size_t)c0 * 48;
+            const unsigned g = (unsigned)ceil_div(M0, 128);
+            if (img_mode == PB200_IMG_U8_NHWC) vq_out_block_tp_kernel<2><<<g, 128, sm, st>>>(ws.xa, ow, ob, B, h0, w0, c0, img);
+            else if (img_mode == PB200_IMG_F32_NCHW_CLAMP01) vq_out_block_tp_kernel<1><<<g, 128, sm, st>>>(ws.xa, ow, ob, B, h0, w0, c0, img);
+            else vq_out_block_tp_kernel<0><<<g, 128, sm, st>>>(ws.xa, ow, ob, B, h0, w0, c0, img);
+        } else if (img_mode == PB200_IMG_U8_NHWC) vq_out_block_kernel<2><<<ceil_div(M0, 8), 256, 0, st>>>(ws.xa, ow, ob, B, h0, w0, c0, img);
         else if (img_mode == PB200_IMG_F32_NCHW_CLAMP01) vq_out_block_kernel<1><<<ceil_div(M0, 8), 256, 0, st>>>(ws.xa, ow, ob, B, h0, w0, c0, img);
         else vq_out_block_kernel<0><<<ceil_div(M0, 8), 256, 0, st>>>(ws.xa, ow, ob, B, h0, w0, c0, img);
         PB_LAUNCH_CHECK();

@@ -628,6 +628,7 @@ class Paella(nn.Module):
         return feats
 
     def logits_from_features(self, feats: torch.Tensor, batch: int, h: int, w: int) -> torch.Tensor:
+        self._ensure_packed()
         L = lib()
         dev = self._device()
         with torch.cuda.device(dev):
@@ -640,6 +641,7 @@ class Paella(nn.Module):
     def sample_tokens(self, feats: torch.Tensor, batch: int, h: int, w: int, cfg: Optional[float], temperature: float,
                       generator=None) -> torch.Tensor:
         """Fused out_mapper + CFG + temperature + multinomial on torch's random stream (ref/src/utils.py:44-50)."""
+        self._ensure_packed()
         L = lib()
         dev = self._device()
         with torch.cuda.device(dev):

@@ -28,6 +28,18 @@ import test_gpu_attention as ta
 print("attn tc", ta._run(2, 64, 20, 2, 80, True, True, False)[:2])
 print("attn tc P=16", ta._run(2, 16, 12, 2, 80, True, False, True)[:2])
 print("attn mma", ta._run(2, 16, 12, 2, 32, True, True, False)[:2])
+# codec ResBlock front (row statistics + patch kernel), partial patches
+from paella_b200.vqgan import ResBlock
+blk = ResBlock(192, 768).to(DEV).eval()
+print("vq resblock", blk(torch.randn(1, 192, 13, 13, device=DEV, generator=g)).shape)
+torch.cuda.synchronize(); print("sanitizer case 1 done")
+PY
+cat > /tmp/san_case2.py <<'PY'
+import os, sys, math, torch
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+from paella_b200 import _lib, ops
+DEV = "cuda"
+g = torch.Generator(device=DEV).manual_seed(0)
 # sampler + RNG kernels
 from helpers import load_golden
 from paella_b200.modules import Paella
@@ -38,9 +50,11 @@ print("sampler", m.sample_tokens(feats, 2, 8, 8, 4.0, 0.7).shape)
 p = torch.rand(64, 100, device=DEV, generator=g); print("multinomial", ops.multinomial(p).shape)
 t = torch.from_numpy
 print("forward", m(t(gg["x"]).to(DEV), t(gg["r"]).to(DEV), t(gg["byt5"]).to(DEV), clip=t(gg["clip"]).to(DEV)).shape)
-torch.cuda.synchronize(); print("sanitizer case done")
+torch.cuda.synchronize(); print("sanitizer case 2 done")
 PY
 for tool in memcheck racecheck; do
-  timeout 420 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py > $O/${TAG}_${tool}.log 2>&1
-  echo "$tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $O/${TAG}_${tool}.log | tail -1)"
+  for part in "" 2; do
+    timeout 420 compute-sanitizer --tool $tool --print-limit 20 python -X faulthandler /tmp/san_case$part.py > $O/${TAG}_${tool}$part.log 2>&1
+    echo "$tool part ${part:-1} rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $O/${TAG}_${tool}$part.log | tail -1)"
+  done
 done
