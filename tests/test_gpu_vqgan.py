@@ -122,6 +122,27 @@ def test_f4_roundtrip_vs_oracle(f4):
     assert dec_err < 1e-3
 
 
+def test_f4_odd_geometry_vs_oracle(f4):
+    """24 x 36 images: half-resolution width 18 (a partial 4-position group of the in_block kernel), latent 6 x 9 (partial 2 x 8
+    patches and clamped halos of the fused ResBlock front), 216 positions per image for the thread-per-position out_block."""
+    from oracle import vqgan_oracle as vo
+    m, sd = f4
+    img = torch.rand(3, 3, 24, 36, generator=torch.Generator().manual_seed(11))
+    lat_want = vo.encode_latents(sd, img)                       # NHWC [3,6,9,4]
+    qe, xs, idx, _ = m.encode(img.to(DEV))
+    lat = (xs * m.scale_factor).permute(0, 2, 3, 1).cpu()
+    lat_err = float((lat - lat_want).abs().max())
+    dec_want = vo.decode_indices(sd, idx.cpu())
+    dec = m.decode_indices(idx).cpu()
+    dec_err = float((dec - dec_want).abs().max())
+    u8 = m.decode_indices_u8(idx).cpu()
+    want_u8 = dec.clamp(0, 1).mul(255).add_(0.5).clamp_(0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+    _log("f4_odd_geometry", {"latent_max_abs": lat_err, "decode_max_abs": dec_err})
+    assert idx.shape == (3, 6, 9) and dec.shape == (3, 3, 24, 36)
+    assert lat_err < 2e-2 and dec_err < 1e-3
+    assert torch.equal(u8, want_u8)
+
+
 def test_f4_large_batch_roundtrip_properties(f4):
     """BASELINE config 5 shape (reduced batch): decode(encode(x)) is deterministic and encode is idempotent on
     indices -> codebook vectors."""
